@@ -1,0 +1,206 @@
+"""ctypes binding of libpsfr_b200.so (C ABI in include/psfr.h).
+
+The product path has no CPU fallback: if the shared library is missing, cannot be
+loaded, or no CUDA device is present, every entry point raises ``PsfrError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpsfr_b200.so')
+
+# record layouts (keep in sync with include/psfr.h)
+DRAW_R0, DRAW_L0, DRAW_CPHI_0, DRAW_CPHI_1, DRAW_H_0, DRAW_H_1 = 0, 1, 2, 3, 4, 5
+DRAW_WX_0, DRAW_WY_0, DRAW_WX_1, DRAW_WY_1, DRAW_FITC, DRAW_ALPHA_TT, DRAW_NLAYERS = 6, 7, 8, 9, 10, 11, 12
+DRAW_NPAR = 16
+FIT_PEAK, FIT_Y0, FIT_X0, FIT_ALPHA, FIT_N, FIT_FWHM, FIT_CHISQ, FIT_ITER = range(8)
+FIT_ERR_PEAK, FIT_ERR_Y0, FIT_ERR_X0, FIT_ERR_ALPHA, FIT_ERR_N, FIT_ERR_FWHM, FIT_FLUX = range(8, 15)
+FIT_NPAR = 16
+AO_DIM = 80
+PSF_DIM = 40
+
+E_CUDA, E_ARG, E_UNSUPPORTED, E_CAPACITY, E_STATE = -1, -2, -3, -4, -5
+
+
+class PsfrError(RuntimeError):
+    """Failure reported by the CUDA library (or the library itself is unavailable)."""
+
+    def __init__(self, code, msg):
+        super().__init__('psfr error %d: %s' % (code, msg))
+        self.code = code
+
+
+_lib = None
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_D = ctypes.c_double
+
+_SIGNATURES = {
+    'psfr_create': (_I, [_I, _I, _I, _I, ctypes.POINTER(_P)]),
+    'psfr_destroy': (None, [_P]),
+    'psfr_last_error': (ctypes.c_char_p, [_P]),
+    'psfr_version': (_I, []),
+    'psfr_set_geometry': (_I, [_P, _P, _P, _P]),
+    'psfr_psd': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P]),
+    'psfr_load_psd': (_I, [_P, _I, _P, _P]),
+    'psfr_structure_function': (_I, [_P, _I, _P]),
+    'psfr_psd_to_psf': (_I, [_P, _I, _D, _P, _P]),
+    'psfr_psf_cube': (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    'psfr_convolve': (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    'psfr_moffat_fit': (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    'psfr_compute_batch': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
+    'psfr_mean_refit': (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    'psfr_polyfit': (_I, [_P, _I, _I, _P, _I, _P, _P, _P]),
+    'psfr_get_otf': (_I, [_P, _P]),
+    'psfr_get_structure_function': (_I, [_P, _I, _P]),
+    'psfr_kernel_launches': (ctypes.c_longlong, [_P]),
+    'psfr_last_hot_timing': (_I, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I), ctypes.POINTER(ctypes.c_longlong)]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU tests)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (once).  Raises PsfrError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsfrError(E_STATE, 'libpsfr_b200.so is not built (run `python -m muse_psfr_b200.build`); '
+                                 'there is no CPU fallback')
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:  # pragma: no cover - depends on the host
+        raise PsfrError(E_STATE, 'cannot load %s: %s' % (LIB_PATH, exc))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    """Raw address of a numpy array, a torch tensor (device or host), an int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        if not a.flags['C_CONTIGUOUS']:
+            raise ValueError('array must be C-contiguous')
+        return a.ctypes.data
+    if hasattr(a, 'data_ptr'):  # torch tensor used purely as a buffer carrier
+        if not a.is_contiguous():
+            raise ValueError('tensor must be contiguous')
+        return a.data_ptr()
+    raise TypeError('unsupported buffer type %r' % type(a))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One psfr_ctx: twiddles, telescope OTF and workspaces on one GPU."""
+
+    def __init__(self, device=0, dim=1280, max_planes=16, max_lambda=35):
+        lib = load()
+        handle = _P()
+        rc = lib.psfr_create(int(device), int(dim), int(max_planes), int(max_lambda), ctypes.byref(handle))
+        if rc != 0:
+            msg = lib.psfr_last_error(None).decode()
+            raise PsfrError(rc, msg)
+        self._h = handle
+        self._lib = lib
+        self.device = int(device)
+        self.dim = int(dim)
+        self.max_planes = int(max_planes)
+        self.max_lambda = int(max_lambda)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.psfr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PsfrError(rc, self._lib.psfr_last_error(self._h).decode())
+
+    # thin wrappers -------------------------------------------------------------------
+    def set_geometry(self, f, f_x, f_y):
+        f, f_x, f_y = f64(f), f64(f_x), f64(f_y)
+        self._check(self._lib.psfr_set_geometry(self._h, ptr(f), ptr(f_x), ptr(f_y)))
+
+    def psd(self, draws, dirs, poslgs, out=None, stream=None):
+        draws, dirs, poslgs = f64(draws), f64(dirs), f64(poslgs)
+        self._check(self._lib.psfr_psd(self._h, draws.shape[0], ptr(draws), dirs.shape[1], ptr(dirs),
+                                       poslgs.shape[1], ptr(poslgs), ptr(out), stream))
+
+    def load_psd(self, psd, nplanes, stream=None):
+        self._check(self._lib.psfr_load_psd(self._h, int(nplanes), ptr(psd), stream))
+
+    def structure_function(self, nplanes, stream=None):
+        self._check(self._lib.psfr_structure_function(self._h, int(nplanes), stream))
+
+    def psd_to_psf(self, plane, lambda_m, out, stream=None):
+        self._check(self._lib.psfr_psd_to_psf(self._h, int(plane), float(lambda_m), ptr(out), stream))
+
+    def psf_cube(self, ndraw, ndir, lambda_nm, out, stream=None):
+        lam = f64(lambda_nm)
+        self._check(self._lib.psfr_psf_cube(self._h, int(ndraw), int(ndir), lam.size, ptr(lam), ptr(out), stream))
+
+    def convolve(self, ndraw, lambda_nm, alpha_tt, cube, out, stream=None):
+        lam, att = f64(lambda_nm), f64(alpha_tt)
+        self._check(self._lib.psfr_convolve(self._h, int(ndraw), lam.size, ptr(lam), ptr(att), ptr(cube),
+                                            ptr(out), stream))
+
+    def moffat_fit(self, nimg, ny, nx, imgs, params, stream=None):
+        self._check(self._lib.psfr_moffat_fit(self._h, int(nimg), int(ny), int(nx), ptr(imgs), ptr(params), stream))
+
+    def compute_batch(self, draws, dirs, poslgs, lambda_nm, out_cube=None, out_fit=None, stream=None):
+        if not hasattr(draws, 'data_ptr'):      # numpy / sequence; torch tensors pass through as buffers
+            draws = f64(draws)
+        dirs, poslgs, lam = f64(dirs), f64(poslgs), f64(lambda_nm)
+        self._check(self._lib.psfr_compute_batch(self._h, draws.shape[0], ptr(draws), dirs.shape[1], ptr(dirs),
+                                                 poslgs.shape[1], ptr(poslgs), lam.size, ptr(lam),
+                                                 ptr(out_cube), ptr(out_fit), stream))
+
+    def mean_refit(self, ncube, nlam, cubes, out_mean=None, out_fit=None, stream=None):
+        self._check(self._lib.psfr_mean_refit(self._h, int(ncube), int(nlam), ptr(cubes), ptr(out_mean),
+                                              ptr(out_fit), stream))
+
+    def polyfit(self, lambda_nm, deg, y, stream=None):
+        lam, y = f64(lambda_nm), f64(np.atleast_2d(y))
+        coef = np.empty((y.shape[0], deg + 1))
+        self._check(self._lib.psfr_polyfit(self._h, y.shape[0], lam.size, ptr(lam), int(deg), ptr(y), ptr(coef), stream))
+        return coef
+
+    def get_otf(self):
+        out = np.empty((self.dim // 2 + 2, self.dim))
+        self._check(self._lib.psfr_get_otf(self._h, ptr(out)))
+        return out
+
+    def get_structure_function(self, plane):
+        out = np.empty((self.dim // 2 + 2, self.dim))
+        self._check(self._lib.psfr_get_structure_function(self._h, int(plane), ptr(out)))
+        return out
+
+    def kernel_launches(self):
+        return int(self._lib.psfr_kernel_launches(self._h))
+
+    def last_hot_timing(self):
+        ms, n, psfs = _D(), _I(), ctypes.c_longlong()
+        self._check(self._lib.psfr_last_hot_timing(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(psfs)))
+        return ms.value, n.value, psfs.value

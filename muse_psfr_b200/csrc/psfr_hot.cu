@@ -1,0 +1,265 @@
+// Stage B, pruned: the hot path of psf_muse / psd_to_psf (psfrec.py:667-685, 792-801).
+//
+// For every (plane, wavelength) the reference builds OTF = exp(-Dphi/2) * OTF_tel on the
+// full N x N grid, inverse-transforms it and then reads only 80 rows x 80 columns of the
+// result (bilinear resampling to 40 x 40).  Here:
+//
+//  * hot_rows_kernel  - persistent, one CTA per SM.  Row pairs of the structure function D
+//    (and of the telescope OTF) stream into a shared-memory ring with TMA bulk copies
+//    (cp.async.bulk + mbarrier complete_tx), issued by whichever warp releases a stage
+//    last; eight warps each take one wavelength at a time: OTF rows = exp(-c_lambda D) * T
+//    evaluated straight from shared memory into registers, one 1280-point warp FFT for the two packed real rows,
+//    and only the 80 sampled frequencies (+ mirrors) are untangled and written, as one
+//    32-byte sector per frequency.  D is read from HBM/L2 once per row pair for ALL
+//    wavelengths; the N x N OTF and PSF grids never exist in memory.
+//  * hot_cols pass    - 40 Hermitian column-pair transforms per PSF (summing the field
+//    directions of a draw before the transform: the mean over directions, psfrec.py:674,
+//    commutes with the linear transform), keeping the 80 sampled outputs -> 80x80 samples.
+#include "pass_kernel.cuh"
+
+namespace psfr {
+
+constexpr int kHotWarps = 8;   // consumer warps
+constexpr int kStages = 3;     // ring depth
+constexpr int kTile = 2 * kN;  // doubles per tile (two rows)
+constexpr uint32_t kTileBytes = kTile * sizeof(double);
+constexpr size_t kHotSmem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
+                            (size_t)kStages * 2 * kTileBytes + (size_t)kHotWarps * G::XBUF * sizeof(double);
+static_assert(kHotSmem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+int hot_event(Ctx* c, int which, cudaStream_t s);   // psfr_api.cu: CUDA-event bracket of the row kernel
+
+struct HotParams {
+    const double* D;       // [nplanes][kRows][N]
+    const double* T;       // [kRows][N]
+    double2* Y;            // [nplanes][nlam][kNS][kRows]
+    const double* clam;    // [nlam]
+    const uint16_t* kidx;  // [nlam][kNS]
+    int nplanes, nlam;
+};
+
+__global__ void __launch_bounds__(kHotWarps * 32, 1)
+hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    int* released = reinterpret_cast<int*>(full + kStages);   // per-stage count of warps done with it
+    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
+    double2* tw2 = tw1 + G::TW1;
+    double* ring = reinterpret_cast<double*>(tw2 + G::TW2);   // [stage][D tile | T tile]
+    double* xall = ring + (size_t)kStages * 2 * kTile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // static partition of the (plane, row pair) items over the persistent CTAs
+    const int items = p.nplanes * kPairs;
+    const int per = items / gridDim.x, rem = items % gridDim.x;
+    const int begin = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int count = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+    // TMA bulk loads of item `it` (two rows of D and of the telescope OTF) into its ring stage
+    auto issue = [&](int it) {
+        const int s = it % kStages;
+        const int item = begin + it;
+        const int plane = item / kPairs, rp = item % kPairs;
+        double* dst = ring + (size_t)s * 2 * kTile;
+        mbar_expect_tx(full + s, 2 * kTileBytes);
+        tma_load_1d(dst, p.D + ((size_t)plane * kRows + 2 * rp) * kN, kTileBytes, full + s);
+        tma_load_1d(dst + kTile, p.T + (size_t)(2 * rp) * kN, kTileBytes, full + s);
+    };
+
+    for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            released[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int it = 0; it < kStages && it < count; ++it) issue(it);
+    }
+    __syncthreads();
+
+    double* xb = xall + (size_t)warp * G::XBUF;
+    for (int it = 0; it < count; ++it) {
+        const int s = it % kStages, u = it / kStages;
+        // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
+        int lam = (warp - (int)(((long long)it * p.nlam) % kHotWarps) + kHotWarps) % kHotWarps;
+        if (lam < p.nlam) {
+            mbar_wait(full + s, u & 1);
+            const double* sD = ring + (size_t)s * 2 * kTile;
+            const double* sT = sD + kTile;
+            const int item = begin + it;
+            const int plane = item / kPairs, rp = item % kPairs;
+            for (; lam < p.nlam; lam += kHotWarps) {
+                const double c = __ldg(p.clam + lam);
+                double2 v[40];
+#pragma unroll
+                for (int i = 0; i < 40; ++i) {
+                    const int n = slot_n(i, lane);
+                    const double t1 = sT[n], t2 = sT[kN + n];
+                    // outside the pupil-autocorrelation support the OTF is exactly zero
+                    if (__all_sync(0xffffffffu, (t1 == 0.0) & (t2 == 0.0))) {
+                        v[i] = make_double2(0.0, 0.0);
+                    } else {
+                        v[i] = make_double2(exp(-c * sD[n]) * t1, exp(-c * sD[kN + n]) * t2);
+                    }
+                }
+                warp_fft<kR3>(v, xb, tw1, tw2, lane);
+                // gather the sampled frequencies kA and their mirrors kB = -kA
+                const uint16_t* kx = p.kidx + (size_t)lam * kNS;
+                double2 za[3], zb[3];
+                int ka[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
+#pragma unroll
+                for (int cpt = 0; cpt < 2; ++cpt) {
+                    fft_dump<kR3>(v, xb, lane, cpt);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        comp_set(za[i], cpt, xb[nat_addr(ka[i])]);
+                        comp_set(zb[i], cpt, xb[nat_addr((kN - ka[i]) % kN)]);
+                    }
+                    __syncwarp();
+                }
+                double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int y = lane + 32 * i;
+                    if (y < kNS) {
+                        double2* o = out + (size_t)y * kRows;
+                        o[0] = make_double2(0.5 * (za[i].x + zb[i].x), 0.5 * (za[i].y - zb[i].y));
+                        o[1] = make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x));
+                    }
+                }
+            }
+        }
+        // release the stage; the last warp to do so refills it with item it + kStages
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int old = atomicAdd(released + s, 1);
+            if (old == kHotWarps - 1) {
+                atomicExch(released + s, 0);
+                if (it + kStages < count) {
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(it + kStages);
+                }
+            }
+        }
+    }
+}
+
+// ---------------- pruned column pass
+// line f = ((draw*nlam + lam)*40 + m): sampled rows 2m, 2m+1 of that PSF, summed over the
+// ndir planes of the draw, Hermitian-extended along the half-plane row index.
+struct LoadSampledPair {
+    const double2* Y;  // [nplanes][nlam][kNS][kRows]
+    int nlam, ndir;
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const int m = f % (kNS / 2), img = f / (kNS / 2);
+        const int lam = img % nlam, draw = img / nlam;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) v[i] = make_double2(0.0, 0.0);
+        for (int d = 0; d < ndir; ++d) {
+            const double2* c1 = Y + (((size_t)(draw * ndir + d) * nlam + lam) * kNS + 2 * m) * kRows;
+            const double2* c2 = c1 + kRows;
+#pragma unroll
+            for (int i = 0; i < 40; ++i) {
+                const int n = slot_n(i, lane);
+                if (n <= kNH) {
+                    const double2 r1 = __ldg(c1 + n), r2 = __ldg(c2 + n);
+                    v[i].x += r1.x - r2.y;
+                    v[i].y += r1.y + r2.x;
+                } else {
+                    const double2 r1 = __ldg(c1 + (kN - n)), r2 = __ldg(c2 + (kN - n));
+                    v[i].x += r1.x + r2.y;
+                    v[i].y += r2.x - r1.y;
+                }
+            }
+        }
+    }
+};
+
+// samples S[img][i][j] = scale * (-1)^(X_i + Y_j) * F[xi_i, eta_j]
+struct StoreSamples {
+    double* S;             // [nimg][kNS][kNS]
+    const uint16_t* kidx;  // [nlam][kNS]
+    int nlam;
+    double scale;
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        const int m = f % (kNS / 2), img = f / (kNS / 2);
+        const int lam = img % nlam;
+        const uint16_t* kx = kidx + (size_t)lam * kNS;
+        const int k1 = __ldg(kx + 2 * m), k2 = __ldg(kx + 2 * m + 1);
+        double* o = S + ((size_t)img * kNS + 2 * m) * kNS;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int j = lane + 32 * i;
+            if (j < kNS) {
+                const int kj = __ldg(kx + j);
+                const double2 z = nat_get(xb, kj);
+                o[j] = (((k1 + kj) & 1) ? -scale : scale) * z.x;
+                o[kNS + j] = (((k2 + kj) & 1) ? -scale : scale) * z.y;
+            }
+        }
+    }
+};
+
+int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PSFR_CUDA(c, cudaFuncSetAttribute(hot_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kHotSmem));
+        attr_set = true;
+    }
+    const int nplanes = ndraw * ndir;
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, nplanes, nlam};
+    int grid = c->sm_count;
+    if (grid > nplanes * kPairs) grid = nplanes * kPairs;
+    int rc = hot_event(c, 0, s);
+    if (rc) return rc;
+    hot_rows_kernel<<<grid, kHotWarps * 32, kHotSmem, s>>>(p, c->d_tw);
+    PSFR_LAUNCH_CHECK(c);
+    if ((rc = hot_event(c, 1, s))) return rc;
+    c->hot_launches += 1;
+    c->hot_psfs += (long long)nplanes * nlam;
+    // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
+    // inverse transform); psf_muse averages the directions.
+    const double scale = 1.0 / ndir;
+    return launch_pass(c, LoadSampledPair{c->d_ybuf, nlam, ndir},
+                       StoreSamples{c->d_samp, c->d_kidx, nlam, scale}, ndraw * nlam * (kNS / 2), s);
+}
+
+}  // namespace psfr

@@ -1,0 +1,125 @@
+// Internal declarations shared by the translation units of libpsfr_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/psfr.h"
+
+namespace psfr {
+
+constexpr int kR3 = 20;                 // N = 64*R3 = 1280
+constexpr int kN = 64 * kR3;
+constexpr int kNH = kN / 2;             // 640
+constexpr int kRows = kNH + 2;          // half-plane rows 0..640 plus one zero pad row
+constexpr int kPairs = kRows / 2;       // 321 row pairs
+constexpr int kAO = PSFR_AO_DIM;        // 80
+constexpr int kPSF = PSFR_PSF_DIM;      // 40
+constexpr int kNS = 2 * kPSF;           // 80 sampled rows / columns per PSF
+constexpr int kKW = 41;                 // Moffat kernel width
+constexpr int kMaxGS = 4;
+constexpr int kMaxDir = 256;            // field directions per draw
+constexpr int kMaxLambdaCap = 4096;
+
+// layout of the small scratch array d_misc (doubles)
+constexpr int kMiscDirs = 0;            // [2][ndir]
+constexpr int kMiscPos = 1024;          // [2][ngs]
+constexpr int kMiscTwo = 2048;          // the constant 2.0
+constexpr int kMiscMuse = 4096;         // gamma[nlam], beta[nlam] of the MUSE kernels
+constexpr int kMiscCentre = 16384;      // [max_planes] structure-function centres
+inline int misc_alpha_tt(int max_planes) { return kMiscCentre + max_planes; }   // [max_planes]
+inline int misc_size(int max_planes) { return kMiscCentre + 2 * max_planes + 64; }
+
+struct Ctx {
+    int device = 0;
+    int N = kN;
+    int max_planes = 0;
+    int max_lambda = 0;
+    int sm_count = 148;
+    long long launches = 0;
+    bool geometry_set = false;
+    int planes_loaded = 0;       // planes whose PSD sits in d_psd
+    int planes_struct = 0;       // planes whose structure function sits in d_dphi
+    double pup_sum = 0;
+
+    double2* d_tw = nullptr;     // twiddles: TW1 then TW2
+    double* d_pup = nullptr;     // [N/2][N/2] pupil as doubles
+    double* d_otf = nullptr;     // [kRows][N] telescope OTF half-plane (centred, pad row zero)
+    double* d_geom = nullptr;    // f, f_x, f_y: 3 x 80 x 80
+    double* d_psd = nullptr;     // [max_planes][N][N]
+    double2* d_bt = nullptr;     // [max_planes][N][kRows] transposed row-pass output (full mode)
+    double* d_dphi = nullptr;    // [max_planes][kRows][N] structure function (transposed half-plane)
+    double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][kRows] pruned row-pass output
+    double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples
+    double* d_ao = nullptr;      // [max_planes][80][80] AO-zone PSD (centred, reference orientation)
+    double* d_draws = nullptr;   // [max_planes][PSFR_DRAW_NPAR]
+    double* d_misc = nullptr;    // small: dirs, poslgs, lambda tables ...
+    double* d_lam = nullptr;     // [max_lambda] c_lambda = 0.5 (2 pi/lambda_nm)^2
+    uint16_t* d_kidx = nullptr;  // [max_lambda][kNS] sampled output indices (shifted by N/2)
+    double* d_frac = nullptr;    // [max_lambda][kPSF] bilinear fractions
+    double* d_kern_tt = nullptr; // [max_planes][41][41] normalised tip-tilt kernels
+    double* d_kern_mu = nullptr; // [max_lambda][41][41] normalised MUSE kernels
+    double* d_cube = nullptr;    // [max_planes*max_lambda][40][40] staging for cubes
+    double* d_cube2 = nullptr;   // second staging buffer
+    double* d_fit = nullptr;     // [max_planes*max_lambda][PSFR_FIT_NPAR]
+    double* d_stage = nullptr;   // generic staging for host inputs (max_planes*N*N doubles)
+    double* d_poly = nullptr;    // polynomial fit scratch
+    void* h_pinned = nullptr;    // pinned bounce buffer
+    size_t h_pinned_bytes = 0;
+
+    cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;
+    int hot_launches = 0;
+    long long hot_psfs = 0;
+    bool hot_timed = false;
+
+    char err[512] = {0};
+};
+
+int set_error(Ctx* c, int code, const char* fmt, ...);
+
+#define PSFR_CUDA(ctx, call)                                                             \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return psfr::set_error((ctx), PSFR_E_CUDA, "%s failed at %s:%d: %s", #call,  \
+                                   __FILE__, __LINE__, cudaGetErrorString(e__));         \
+    } while (0)
+
+#define PSFR_LAUNCH_CHECK(ctx)                                                           \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess)                                                          \
+            return psfr::set_error((ctx), PSFR_E_CUDA, "kernel launch failed at %s:%d: %s", \
+                                   __FILE__, __LINE__, cudaGetErrorString(e__));         \
+    } while (0)
+
+// ---- psfr_passes.cu: generic row/column FFT passes ----------------------------------
+// stage A (PSD -> D_unit) on planes [0, nplanes) of the workspace
+int run_structure_function(Ctx* c, int nplanes, cudaStream_t s);
+// full-grid stage B: plane `plane`, exponent scale clam -> d_psd-sized output in `out_dev`
+int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s);
+// context init: pupil + telescope OTF
+int run_build_otf(Ctx* c, cudaStream_t s);
+
+// ---- psfr_hot.cu: pruned stage B ----------------------------------------------------
+// row pass with fused exp(-c D) * OTF for nplanes x nlam, then pruned column pass summing
+// the ndir planes of each draw into d_samp [ndraw*nlam][80][80]
+int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s);
+
+// ---- psfr_psd.cu ---------------------------------------------------------------------
+int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s);  // uses d_draws, d_misc
+
+// ---- psfr_plane.cu -------------------------------------------------------------------
+int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host, bool tt, bool mu,
+                      cudaStream_t s);
+// samples -> 40x40 resampled + normalised cube (psf_muse tail)
+int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s);
+// two Moffat convolutions; img index = draw*nlam + lam
+int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s);
+int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s);
+int run_mean(Ctx* c, int ncube, int plane_elems, const double* cubes_dev, double* out_dev,
+             cudaStream_t s);
+int run_polyfit(Ctx* c, int nseries, int nlam, int deg, const double* lb_dev, const double* y_dev,
+                double* coef_dev, cudaStream_t s);
+
+}  // namespace psfr

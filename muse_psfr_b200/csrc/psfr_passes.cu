@@ -1,0 +1,257 @@
+// Generic FFT passes built on the warp transform: each warp loads one length-N line
+// (two real lines packed as re/im, or a Hermitian-extended pair of half columns),
+// transforms it, and writes either the transposed, untangled half-spectrum or two real
+// output rows.  Used for
+//   stage A  : PSD -> structure function D_unit     (psfrec.py:717-722)
+//   stage B  : full-grid OTF -> PSF (parity mode)   (psfrec.py:792-801)
+//   init     : pupil -> telescope OTF               (psfrec.py:784-790)
+// A 2-D transform is two passes; the first writes its output transposed in 32-byte
+// sectors, the second reads contiguous lines again, so no stand-alone transpose exists.
+#include "pass_kernel.cuh"
+
+namespace psfr {
+
+// ------------------------------------------------------------------ loaders
+// E = (P + P reflected)/2 on rows (2rp, 2rp+1) of plane f / kPairs: real-even input whose
+// transform is Re of the transform of P (psfrec.py:718,721 keeps only bg.real).
+struct LoadEvenRows {
+    const double* P;  // [nplanes][N][N]
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const int plane = f / kPairs, rp = f % kPairs;
+        const int a1 = 2 * rp, a2 = a1 + 1;
+        const double* base = P + (size_t)plane * kN * kN;
+        const double* r1 = base + (size_t)a1 * kN;
+        const double* r1m = base + (size_t)((kN - a1) % kN) * kN;
+        const bool ok2 = a2 <= kNH;
+        const double* r2 = base + (size_t)(ok2 ? a2 : 0) * kN;
+        const double* r2m = base + (size_t)(ok2 ? (kN - a2) : 0) * kN;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            const int nm = (kN - n) % kN;
+            const double e1 = 0.5 * (__ldg(r1 + n) + __ldg(r1m + nm));
+            const double e2 = ok2 ? 0.5 * (__ldg(r2 + n) + __ldg(r2m + nm)) : 0.0;
+            v[i] = make_double2(e1, e2);
+        }
+    }
+};
+
+// rows (2rp, 2rp+1) of exp(-c D) * OTF on the transposed half-plane (psfrec.py:793-797)
+struct LoadOtfRows {
+    const double* D;   // [kRows][N] of the selected plane
+    const double* T;   // [kRows][N]
+    double c;
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const double* d1 = D + (size_t)(2 * f) * kN;
+        const double* t1 = T + (size_t)(2 * f) * kN;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            v[i] = make_double2(exp(-c * __ldg(d1 + n)) * __ldg(t1 + n),
+                                exp(-c * __ldg(d1 + kN + n)) * __ldg(t1 + kN + n));
+        }
+    }
+};
+
+// pupil rows (2f, 2f+1), zero-padded to N columns (psfrec.py:784-787)
+struct LoadPupilRows {
+    const double* pup;  // [N/2][N/2]
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const double* p1 = pup + (size_t)(2 * f) * kNH;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            v[i] = n < kNH ? make_double2(__ldg(p1 + n), __ldg(p1 + kNH + n)) : make_double2(0., 0.);
+        }
+    }
+};
+
+// Hermitian-extended pair of half columns: line f = (plane, m) reads buffer rows
+// y(2m), y(2m+1) with y(a) = (a + N/2) % N and forms R[.,y1] + i R[.,y2] over all N rows,
+// R[N-a] = conj(R[a]).  The transform of that line is real-in-two-halves: Re -> output
+// row 2m, Im -> output row 2m+1.
+struct LoadHermitianPair {
+    const double2* Bt;  // [nplanes][N][kRows]
+    int npair;          // pairs per plane
+    int last_valid;     // largest valid output row (the partner of an invalid row is duplicated)
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const int plane = f / npair, m = f % npair;
+        const int o1 = 2 * m, o2 = (2 * m + 1 <= last_valid) ? 2 * m + 1 : o1;
+        const double2* c1 = Bt + ((size_t)plane * kN + (o1 + kNH) % kN) * kRows;
+        const double2* c2 = Bt + ((size_t)plane * kN + (o2 + kNH) % kN) * kRows;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            if (n <= kNH) {
+                const double2 r1 = __ldg(c1 + n), r2 = __ldg(c2 + n);
+                v[i] = make_double2(r1.x - r2.y, r1.y + r2.x);
+            } else {
+                const double2 r1 = __ldg(c1 + (kN - n)), r2 = __ldg(c2 + (kN - n));
+                v[i] = make_double2(r1.x + r2.y, r2.x - r1.y);
+            }
+        }
+    }
+};
+
+// single complex column y = f, rows >= nrows are zero (forward transform of the padded pupil)
+struct LoadColumnPadded {
+    const double2* Bt;  // [N][kRows]
+    int nrows;
+    __device__ void operator()(int f, int lane, double2* v) const {
+        const double2* c1 = Bt + (size_t)f * kRows;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            v[i] = n < nrows ? __ldg(c1 + n) : make_double2(0., 0.);
+        }
+    }
+};
+
+// ------------------------------------------------------------------ storers
+// untangle the two real lines and write them transposed: Bt[plane][y][2rp], [2rp+1]
+struct StoreTransposedPair {
+    double2* Bt;  // [nplanes][N][kRows]
+    int npair;
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        const int plane = f / npair, rp = f % npair;
+        double2* out = Bt + (size_t)plane * kN * kRows + 2 * rp;
+#pragma unroll 4
+        for (int i = 0; i < 40; ++i) {
+            const int y = lane + 32 * i;
+            const double2 za = nat_get(xb, y), zb = nat_get(xb, (kN - y) % kN);
+            double2* o = out + (size_t)y * kRows;
+            o[0] = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
+            o[1] = make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x));
+        }
+    }
+};
+
+// Re -> row 2m, Im -> row 2m+1 of out[plane][nrows_out][N], column b = (x + N/2) % N,
+// value * scale * (-1)^(row + b)
+struct StoreRealRows {
+    double* out;
+    int npair, nrows_out, last_valid;
+    double scale;
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        const int plane = f / npair, m = f % npair;
+        const int o1 = 2 * m, o2 = o1 + 1;
+        double* r1 = out + ((size_t)plane * nrows_out + o1) * kN;
+        const bool ok2 = o2 <= last_valid;
+#pragma unroll 4
+        for (int i = 0; i < 40; ++i) {
+            const int b = lane + 32 * i;
+            const double2 z = nat_get(xb, (b + kNH) % kN);
+            const double s1 = ((o1 + b) & 1) ? -scale : scale;
+            r1[b] = s1 * z.x;
+            if (ok2) r1[kN + b] = -s1 * z.y;
+        }
+    }
+};
+
+// |Z[x]|^2 -> out[y = f][x]
+struct StoreAbs2 {
+    double* out;  // [N][N]
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        double* r = out + (size_t)f * kN;
+#pragma unroll 4
+        for (int i = 0; i < 40; ++i) {
+            const int x = lane + 32 * i;
+            const double2 z = nat_get(xb, x);
+            r[x] = z.x * z.x + z.y * z.y;
+        }
+    }
+};
+
+// ------------------------------------------------------------------ small elementwise kernels
+__global__ void pupil_kernel(double* pup, double radius, double oc) {
+    // pupil_mask(N/4, N/2, oc) (psfrec.py:190-203): rho = hypot(x-c, y-c)/radius
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kNH * kNH) return;
+    const int y = idx / kNH, x = idx % kNH;
+    const double cc = (kNH - 1) / 2.0;
+    const double rho = hypot(y - cc, x - cc) / radius;
+    pup[idx] = (rho < 1.0 && rho >= oc) ? 1.0 : 0.0;
+}
+
+// T = rint(autocorrelation counts) / (N^2 * sum(pupil)), pad row zero
+__global__ void finalize_otf_kernel(double* t, double inv_norm) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)kRows * kN) return;
+    t[idx] = (idx >= (size_t)(kNH + 1) * kN) ? 0.0 : rint(t[idx]) * inv_norm;
+}
+
+// ------------------------------------------------------------------ drivers
+__global__ void stash_centre_kernel(const double* d, double* centre, int nplanes) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nplanes) centre[p] = d[(size_t)p * kRows * kN + (size_t)kNH * kN + kNH];
+}
+
+// D[a][b] = Draw[N/2][N/2] - Draw[a][b], pad row zero (psfrec.py:721: 2*(bg[0,0] - bg))
+__global__ void finalize_dphi2_kernel(double* d, const double* centre, int nplanes) {
+    const size_t per = (size_t)kRows * kN;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per * nplanes) return;
+    const size_t plane = idx / per, r = idx % per;
+    d[idx] = (r >= (size_t)(kNH + 1) * kN) ? 0.0 : centre[plane] - d[idx];
+}
+
+static int launch_finalize_dphi(Ctx* c, int nplanes, cudaStream_t s) {
+    double* centre = c->d_misc + kMiscCentre;  // scratch area reserved for plane centres
+    stash_centre_kernel<<<(nplanes + 127) / 128, 128, 0, s>>>(c->d_dphi, centre, nplanes);
+    PSFR_LAUNCH_CHECK(c);
+    const size_t total = (size_t)nplanes * kRows * kN;
+    finalize_dphi2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->d_dphi, centre, nplanes);
+    PSFR_LAUNCH_CHECK(c);
+    c->planes_struct = nplanes;
+    return PSFR_OK;
+}
+
+int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
+    // pass 1: rows of the even part of the PSD -> transposed half spectrum
+    int rc = launch_pass(c, LoadEvenRows{c->d_psd}, StoreTransposedPair{c->d_bt, kPairs}, nplanes * kPairs, s);
+    if (rc) return rc;
+    // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
+    const double L = 16.0;
+    rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
+                     StoreRealRows{c->d_dphi, kPairs, kRows, kNH, 2.0 / (L * L)}, nplanes * kPairs, s);
+    if (rc) return rc;
+    return launch_finalize_dphi(c, nplanes, s);
+}
+
+int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s) {
+    const double* D = c->d_dphi + (size_t)plane * kRows * kN;
+    int rc = launch_pass(c, LoadOtfRows{D, c->d_otf, clam}, StoreTransposedPair{c->d_bt, kPairs}, kPairs, s);
+    if (rc) return rc;
+    // psf/psf.sum(): the sum of the raw PSF is the OTF at the origin = 1/N^2 exactly (T centre);
+    // the unnormalised inverse transform carries 1/N^2 as well, so the two cancel.
+    return launch_pass(c, LoadHermitianPair{c->d_bt, kNH, kN - 1},
+                       StoreRealRows{out_dev, kNH, kN, kN - 1, 1.0}, kNH, s);
+}
+
+int run_build_otf(Ctx* c, cudaStream_t s) {
+    pupil_kernel<<<(kNH * kNH + 255) / 256, 256, 0, s>>>(c->d_pup, kN / 4.0, 0.14);
+    PSFR_LAUNCH_CHECK(c);
+    // forward transform of the zero-padded pupil: rows (real pairs) then complex columns -> |.|^2
+    int rc = launch_pass(c, LoadPupilRows{c->d_pup}, StoreTransposedPair{c->d_bt, kNH / 2}, kNH / 2, s);
+    if (rc) return rc;
+    rc = launch_pass(c, LoadColumnPadded{c->d_bt, kNH}, StoreAbs2{c->d_psd}, kN, s);
+    if (rc) return rc;
+    // inverse transform of |P^|^2 (real, even): N^2 x the pupil autocorrelation, centred
+    rc = launch_pass(c, LoadEvenRows{c->d_psd}, StoreTransposedPair{c->d_bt, kPairs}, kPairs, s);
+    if (rc) return rc;
+    rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
+                     StoreRealRows{c->d_otf, kPairs, kRows, kNH, 1.0 / ((double)kN * kN)}, kPairs, s);
+    if (rc) return rc;
+    double centre = 0;
+    PSFR_CUDA(c, cudaMemcpyAsync(&centre, c->d_otf + (size_t)kNH * kN + kNH, sizeof(double),
+                                 cudaMemcpyDeviceToHost, s));
+    PSFR_CUDA(c, cudaStreamSynchronize(s));
+    c->pup_sum = rint(centre);
+    if (!(c->pup_sum > 0)) return set_error(c, PSFR_E_CUDA, "telescope OTF init failed (pupil sum %g)", centre);
+    finalize_otf_kernel<<<(kRows * kN + 255) / 256, 256, 0, s>>>(
+        c->d_otf, 1.0 / ((double)kN * kN * c->pup_sum));
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+}  // namespace psfr

@@ -1,0 +1,568 @@
+// Per-image tail of the path, one CTA per 40 x 40 image:
+//   resample_kernel : clip >= 0, bilinear 80x80 samples -> 40x40, per-plane normalisation
+//                     (psf_muse tail, psfrec.py:679-685 with interpolate :635-641)
+//   convolve_kernel : tip-tilt Moffat (beta = 2) then MUSE intrinsic Moffat, each a
+//                     zero-padded 'same' linear convolution (convolve_final_psf, :911-930)
+//   fit_kernel      : 5-parameter circular Moffat least squares by Levenberg-Marquardt with
+//                     analytic Jacobian (fit_psf_cube -> mpdaf moffat_fit, :861-871)
+//   mean / polyfit  : time mean of cubes (:1104) and polynomial smoothing (:1174-1210)
+#include "psfr_internal.h"
+
+namespace psfr {
+
+constexpr int kImg = kPSF * kPSF;  // 1600
+
+// deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid in all threads
+__device__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;
+}
+
+// ---------------------------------------------------------------- Moffat kernels
+// astropy Moffat2DKernel(gamma, alpha, x_size=41, y_size=41): amplitude (alpha-1)/(pi gamma^2),
+// (1 + r^2/gamma^2)^(-alpha) at integer offsets, normalised to unit sum.
+__global__ void moffat_kernels_kernel(const double* __restrict__ gam, const double* __restrict__ alp,
+                                      int alp_stride, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int k = blockIdx.x;
+    const double g = gam[k], a = alp[k * alp_stride];
+    const double amp = (a - 1) / (3.141592653589793 * g * g);
+    double vals[7];
+    double part = 0.0;
+    int cnt = 0;
+    for (int idx = threadIdx.x; idx < kKW * kKW; idx += blockDim.x, ++cnt) {
+        const int dy = idx / kKW - kKW / 2, dx = idx % kKW - kKW / 2;
+        const double rr = (double)(dx * dx + dy * dy) / (g * g);
+        vals[cnt] = amp * pow(1 + rr, -a);
+        part += vals[cnt];
+    }
+    const double tot = block_sum(part, red);
+    cnt = 0;
+    for (int idx = threadIdx.x; idx < kKW * kKW; idx += blockDim.x, ++cnt)
+        out[(size_t)k * kKW * kKW + idx] = vals[cnt] / tot;
+}
+
+// ---------------------------------------------------------------- resample
+__global__ void __launch_bounds__(256)
+resample_kernel(const double* __restrict__ samp, const double* __restrict__ frac, int nlam,
+                double* __restrict__ cube) {
+    extern __shared__ double dyn_smem[];
+    double* s = dyn_smem;               // kNS*kNS
+    double* red = dyn_smem + kNS * kNS; // 32
+    const int img = blockIdx.x, lam = img % nlam;
+    const double* src = samp + (size_t)img * kNS * kNS;
+    for (int i = threadIdx.x; i < kNS * kNS; i += blockDim.x) s[i] = fmax(src[i], 0.0);   // :680
+    __syncthreads();
+    const double* fr = frac + (size_t)lam * kPSF;
+    double vals[7];
+    double part = 0.0;
+    int cnt = 0;
+    for (int idx = threadIdx.x; idx < kImg; idx += blockDim.x, ++cnt) {
+        const int y = idx / kPSF, x = idx % kPSF;
+        const double fy = fr[y], fx = fr[x];
+        const double* r0 = s + (2 * y) * kNS + 2 * x;
+        const double v = (1 - fy) * ((1 - fx) * r0[0] + fx * r0[1]) +
+                         fy * ((1 - fx) * r0[kNS] + fx * r0[kNS + 1]);
+        vals[cnt] = v;
+        part += v;
+    }
+    const double tot = block_sum(part, red);   // :685
+    cnt = 0;
+    for (int idx = threadIdx.x; idx < kImg; idx += blockDim.x, ++cnt)
+        cube[(size_t)img * kImg + idx] = vals[cnt] / tot;
+}
+
+// ---------------------------------------------------------------- convolution
+// out[i][j] = sum_{i',j'} in[i'][j'] K[i-i'+20][j-j'+20]  (scipy fftconvolve(..., 'same') with a
+// 41x41 kernel = zero-padded linear convolution cropped to the input frame).
+// Thread (ib, j) owns 8 output rows i0..i0+7 of column j; for a fixed input column j' the
+// kernel column K[.][j-j'+20] slides through a register window as i' advances, so each
+// step costs one broadcast load, one kernel load and 8 FMAs.
+constexpr int kKP = 79;  // padded kernel rows: index di + 19, di = i - i' + 20 in [-19, 59]
+
+__device__ void conv_same(const double* __restrict__ in, const double* __restrict__ kp,
+                          double* __restrict__ out) {
+    const int tid = threadIdx.x;
+    if (tid < 5 * kPSF) {
+        const int ib = tid / kPSF, j = tid % kPSF, i0 = 8 * ib;
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+        for (int jp = 0; jp < kPSF; ++jp) {
+            const int dj = j - jp + 20;
+            if (dj < 0 || dj > 40) continue;
+            const double* kc = kp + dj;             // column dj of the padded kernel, row stride 41
+            // window w[u] = Kpad[i0 + u - i' + 20 + 19][dj]; start at i' = 0
+            double w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = kc[(i0 + u + 39) * kKW];
+#pragma unroll
+            for (int ip = 0; ip < kPSF; ++ip) {
+                const double pv = in[ip * kPSF + jp];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = fma(pv, w[u], acc[u]);
+                if (ip + 1 < kPSF) {
+#pragma unroll
+                    for (int u = 7; u > 0; --u) w[u] = w[u - 1];
+                    w[0] = kc[(i0 + 39 - (ip + 1)) * kKW];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) out[(i0 + u) * kPSF + j] = acc[u];
+    }
+}
+
+// load a 41x41 kernel into the zero-padded [79][41] layout
+__device__ void load_kernel_padded(const double* __restrict__ k, double* __restrict__ kp) {
+    for (int idx = threadIdx.x; idx < kKP * kKW; idx += blockDim.x) {
+        const int r = idx / kKW - 19;
+        kp[idx] = (r >= 0 && r < kKW) ? k[r * kKW + idx % kKW] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+convolve_kernel(const double* __restrict__ in, const double* __restrict__ ktt,
+                const double* __restrict__ kmu, int nlam, double* __restrict__ out) {
+    extern __shared__ double dyn_smem[];
+    double* a = dyn_smem;               // kImg
+    double* b = a + kImg;               // kImg
+    double* kp = b + kImg;              // kKP*kKW
+    const int img = blockIdx.x, draw = img / nlam, lam = img % nlam;
+    for (int i = threadIdx.x; i < kImg; i += blockDim.x) a[i] = in[(size_t)img * kImg + i];
+    load_kernel_padded(ktt + (size_t)draw * kKW * kKW, kp);
+    __syncthreads();
+    conv_same(a, kp, b);
+    __syncthreads();
+    load_kernel_padded(kmu + (size_t)lam * kKW * kKW, kp);
+    __syncthreads();
+    conv_same(b, kp, a);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kImg; i += blockDim.x) out[(size_t)img * kImg + i] = a[i];
+}
+
+// ---------------------------------------------------------------- Moffat fit
+// model f = I (1 + ((p-y0)^2 + (q-x0)^2)/a^2)^(-n), parameters x = [I, y0, x0, a, n]
+constexpr int kFitThreads = 128;
+constexpr int kNP = 5;
+constexpr int kNSUM = 21;  // 15 (J^T J upper) + 5 (J^T r) + 1 (cost)
+
+__device__ void block_sum_vec(double* v, int n, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = 0; k < n; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        v[k] = t;
+    }
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < n; ++k) red[warp * kNSUM + k] = v[k];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += red[w * kNSUM + k];
+        v[k] = t;
+    }
+}
+
+// accumulate normal equations at x over this thread's pixels
+__device__ void accumulate(const double* __restrict__ img, int ny, int nx, const double* x, double* sums) {
+    for (int k = 0; k < kNSUM; ++k) sums[k] = 0.0;
+    const double I = x[0], y0 = x[1], x0 = x[2], a = x[3], n = x[4];
+    const double ia2 = 1.0 / (a * a);
+    for (int idx = threadIdx.x; idx < ny * nx; idx += blockDim.x) {
+        const double dp = (double)(idx / nx) - y0, dq = (double)(idx % nx) - x0;
+        const double rho2 = (dp * dp + dq * dq) * ia2;
+        const double uu = 1.0 + rho2;
+        const double lu = log(uu);
+        const double m = exp(-n * lu);             // u^-n
+        const double f = I * m;
+        const double g = 2.0 * n * f / uu;          // 2 I n u^(-n-1)
+        double J[kNP];
+        J[0] = m;
+        J[1] = g * dp * ia2;
+        J[2] = g * dq * ia2;
+        J[3] = g * rho2 / a;
+        J[4] = -f * lu;
+        const double r = f - img[idx];
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < kNP; ++i)
+#pragma unroll
+            for (int j = i; j < kNP; ++j) sums[k++] += J[i] * J[j];
+#pragma unroll
+        for (int i = 0; i < kNP; ++i) sums[15 + i] += J[i] * r;
+        sums[20] += r * r;
+    }
+}
+
+// solve (A + mu diag(A)) d = -g by Cholesky; A from packed upper sums. returns false if not SPD
+__device__ bool solve_damped(const double* s, double mu, double* d) {
+    double A[kNP][kNP];
+    int k = 0;
+    for (int i = 0; i < kNP; ++i)
+        for (int j = i; j < kNP; ++j) {
+            A[i][j] = A[j][i] = s[k++];
+        }
+    for (int i = 0; i < kNP; ++i) A[i][i] *= (1.0 + mu);
+    double L[kNP][kNP];
+    for (int i = 0; i < kNP; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double t = A[i][j];
+            for (int q = 0; q < j; ++q) t -= L[i][q] * L[j][q];
+            if (i == j) {
+                if (!(t > 0.0)) return false;
+                L[i][i] = sqrt(t);
+            } else {
+                L[i][j] = t / L[j][j];
+            }
+        }
+    double y[kNP];
+    for (int i = 0; i < kNP; ++i) {
+        double t = -s[15 + i];
+        for (int q = 0; q < i; ++q) t -= L[i][q] * y[q];
+        y[i] = t / L[i][i];
+    }
+    for (int i = kNP - 1; i >= 0; --i) {
+        double t = y[i];
+        for (int q = i + 1; q < kNP; ++q) t -= L[q][i] * d[q];
+        d[i] = t / L[i][i];
+    }
+    return true;
+}
+
+// diagonal of A^-1 (A SPD from packed sums), via Cholesky; returns false if singular
+__device__ bool inv_diag(const double* s, double* dg) {
+    double A[kNP][kNP], L[kNP][kNP];
+    int k = 0;
+    for (int i = 0; i < kNP; ++i)
+        for (int j = i; j < kNP; ++j) A[i][j] = A[j][i] = s[k++];
+    for (int i = 0; i < kNP; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double t = A[i][j];
+            for (int q = 0; q < j; ++q) t -= L[i][q] * L[j][q];
+            if (i == j) {
+                if (!(t > 0.0)) return false;
+                L[i][i] = sqrt(t);
+            } else {
+                L[i][j] = t / L[j][j];
+            }
+        }
+    for (int c = 0; c < kNP; ++c) {
+        double y[kNP], z[kNP];
+        for (int i = 0; i < kNP; ++i) {
+            double t = (i == c) ? 1.0 : 0.0;
+            for (int q = 0; q < i; ++q) t -= L[i][q] * y[q];
+            y[i] = t / L[i][i];
+        }
+        for (int i = kNP - 1; i >= 0; --i) {
+            double t = y[i];
+            for (int q = i + 1; q < kNP; ++q) t -= L[q][i] * z[q];
+            z[i] = t / L[i][i];
+        }
+        dg[c] = z[c];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kFitThreads)
+fit_kernel(const double* __restrict__ imgs, int ny, int nx, double* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* img = sm;                       // ny*nx
+    double* red = sm + ny * nx;             // 4 * kNSUM
+    double* colw = red + 4 * kNSUM;         // nx
+    __shared__ double xs[kNP];
+    __shared__ int ipk[2];
+    const int npx = ny * nx, tid = threadIdx.x;
+    const double* src = imgs + (size_t)blockIdx.x * npx;
+    for (int i = tid; i < npx; i += blockDim.x) img[i] = src[i];
+    __syncthreads();
+    // ---- start point as mpdaf: peak pixel, width from Image.moments(), n = 2
+    for (int q = tid; q < nx; q += blockDim.x) {
+        double t = 0.0;
+        for (int p = 0; p < ny; ++p) t += p * fabs(img[p * nx + q]);
+        colw[q] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int qb = 0;
+        for (int q = 1; q < nx; ++q)
+            if (colw[q] > colw[qb]) qb = q;
+        double num = 0.0, den = 0.0;
+        for (int p = 0; p < ny; ++p) {
+            const double v = img[p * nx + qb];
+            num += fabs((p - qb) * v);
+            den += fabs(v);
+        }
+        const double wp = sqrt(num / den);
+        int best = 0;
+        for (int i = 1; i < npx; ++i)
+            if (img[i] > img[best]) best = i;
+        ipk[0] = best / nx;
+        ipk[1] = best % nx;
+        const double fwhm0 = wp * 2.0 * sqrt(2.0 * log(2.0));
+        xs[0] = img[best];
+        xs[1] = ipk[0];
+        xs[2] = ipk[1];
+        xs[3] = fwhm0 / (2.0 * sqrt(sqrt(2.0) - 1.0));
+        xs[4] = 2.0;
+    }
+    __syncthreads();
+    double x[kNP], sums[kNSUM], trial[kNSUM], xt[kNP], d[kNP];
+    for (int i = 0; i < kNP; ++i) x[i] = xs[i];
+    accumulate(img, ny, nx, x, sums);
+    block_sum_vec(sums, kNSUM, red);
+    double mu = 1e-3, nu = 2.0;
+    int iter = 0, status = -1;
+    const int max_iter = 200;
+    for (iter = 1; iter <= max_iter; ++iter) {
+        // every thread runs the identical 5x5 solve on identical data
+        bool ok = solve_damped(sums, mu, d);
+        if (!ok) {
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e12) break;
+            continue;
+        }
+        double dn = 0.0, xn = 0.0, pred = 0.0;
+        for (int i = 0; i < kNP; ++i) {
+            xt[i] = x[i] + d[i];
+            const double sc = sqrt(sums[i == 0 ? 0 : i == 1 ? 5 : i == 2 ? 9 : i == 3 ? 12 : 14]);  // |J col|
+            dn += (d[i] * sc) * (d[i] * sc);
+            xn += (x[i] * sc) * (x[i] * sc);
+        }
+        // predicted decrease of the cost r.r : -d.(2 g) - d.A.d = d.(mu D d - g)
+        {
+            const int dia[kNP] = {0, 5, 9, 12, 14};
+            for (int i = 0; i < kNP; ++i) pred += d[i] * (mu * sums[dia[i]] * d[i] - sums[15 + i]);
+        }
+        if (!(xt[3] > 0.0) || !(xt[4] > 0.0) || !isfinite(xt[0])) {
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e12) break;
+            continue;
+        }
+        accumulate(img, ny, nx, xt, trial);
+        block_sum_vec(trial, kNSUM, red);
+        const double actual = sums[20] - trial[20];
+        // near the minimum the cost is flat to rounding: tolerate a noise-level increase so that
+        // Gauss-Newton steps keep contracting, and stop on the (column-scaled) step size
+        const bool small = dn <= 1e-22 * (xn + 1e-300);            // relative step <= 1e-11
+        if (isfinite(trial[20]) && actual >= -1e-13 * sums[20]) {
+            const double rho = pred > 0.0 ? actual / pred : 1.0;
+            for (int i = 0; i < kNP; ++i) x[i] = xt[i];
+            for (int k = 0; k < kNSUM; ++k) sums[k] = trial[k];
+            const double t = 2.0 * rho - 1.0;
+            mu *= fmax(1.0 / 3.0, 1.0 - t * t * t);
+            if (mu < 1e-15) mu = 1e-15;
+            nu = 2.0;
+            if (small) {
+                status = iter;
+                break;
+            }
+        } else {
+            if (dn <= 1e-18 * (xn + 1e-300)) {   // step below 1e-9 relative and no decrease: rounding floor
+                status = iter;
+                break;
+            }
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e15) break;
+        }
+    }
+    if (tid == 0) {
+        double* o = out + (size_t)blockIdx.x * PSFR_FIT_NPAR;
+        const double a = fabs(x[3]), n = x[4];
+        const double kf = 2.0 * sqrt(pow(2.0, 1.0 / n) - 1.0);
+        o[PSFR_FIT_PEAK] = x[0];
+        o[PSFR_FIT_Y0] = x[1];
+        o[PSFR_FIT_X0] = x[2];
+        o[PSFR_FIT_ALPHA] = a;
+        o[PSFR_FIT_N] = n;
+        o[PSFR_FIT_FWHM] = a * kf;
+        o[PSFR_FIT_CHISQ] = sums[20];
+        o[PSFR_FIT_ITER] = (status > 0) ? (double)status : -(double)(iter > max_iter ? max_iter : iter);
+        double dg[kNP];
+        const double dof = (double)(npx - kNP);
+        if (inv_diag(sums, dg)) {
+            double e[kNP];
+            for (int i = 0; i < kNP; ++i) e[i] = sqrt(fabs(dg[i]) * fabs(sums[20] / dof));
+            o[PSFR_FIT_ERR_PEAK] = e[0];
+            o[PSFR_FIT_ERR_Y0] = e[1];
+            o[PSFR_FIT_ERR_X0] = e[2];
+            o[PSFR_FIT_ERR_ALPHA] = e[3];
+            o[PSFR_FIT_ERR_N] = e[4];
+            const double dk = -pow(2.0, 1.0 / n) * log(2.0) / (n * n * sqrt(pow(2.0, 1.0 / n) - 1.0));
+            o[PSFR_FIT_ERR_FWHM] = sqrt((kf * e[3]) * (kf * e[3]) + (a * dk * e[4]) * (a * dk * e[4]));
+        } else {
+            for (int i = PSFR_FIT_ERR_PEAK; i <= PSFR_FIT_ERR_FWHM; ++i) o[i] = nan("");
+        }
+        o[PSFR_FIT_FLUX] = 3.141592653589793 * a * a * x[0] / (n - 1.0);
+        o[15] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- mean of cubes
+__global__ void mean_kernel(const double* __restrict__ cubes, int ncube, size_t elems,
+                            double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= elems) return;
+    // pairwise-free straight sum in input order, then /ncube (np.mean uses pairwise blocks of
+    // 8 along the reduced axis only for contiguous reductions; axis 0 reduces plane by plane)
+    double t = 0.0;
+    for (int k = 0; k < ncube; ++k) t += cubes[(size_t)k * elems + i];
+    out[i] = t / ncube;
+}
+
+// ---------------------------------------------------------------- polynomial smoothing
+// least squares via Householder QR of the shared Vandermonde matrix (columns x^deg .. x^0,
+// as np.polyfit); one thread per series applies Q^T and back-substitutes.
+constexpr int kMaxLam = 256, kMaxDeg = 8;
+__global__ void polyfit_kernel(const double* __restrict__ lb, int nlam, int deg, int nseries,
+                               const double* __restrict__ y, double* __restrict__ coef) {
+    __shared__ double V[kMaxLam * (kMaxDeg + 1)];   // column-major, overwritten by R / reflectors
+    __shared__ double beta[kMaxDeg + 1], rdiag[kMaxDeg + 1];
+    const int nc = deg + 1;
+    for (int idx = threadIdx.x; idx < nlam * nc; idx += blockDim.x) {
+        const int c = idx / nlam, r = idx % nlam;
+        V[c * nlam + r] = pow(lb[r], (double)(deg - c));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < nc; ++c) {
+            double nrm = 0.0;
+            for (int r = c; r < nlam; ++r) nrm += V[c * nlam + r] * V[c * nlam + r];
+            nrm = sqrt(nrm);
+            const double alpha = V[c * nlam + c] > 0 ? -nrm : nrm;
+            V[c * nlam + c] -= alpha;                    // v = x - alpha e1
+            double vv = 0.0;
+            for (int r = c; r < nlam; ++r) vv += V[c * nlam + r] * V[c * nlam + r];
+            beta[c] = vv > 0 ? 2.0 / vv : 0.0;
+            rdiag[c] = alpha;
+            for (int c2 = c + 1; c2 < nc; ++c2) {
+                double dot = 0.0;
+                for (int r = c; r < nlam; ++r) dot += V[c * nlam + r] * V[c2 * nlam + r];
+                dot *= beta[c];
+                for (int r = c; r < nlam; ++r) V[c2 * nlam + r] -= dot * V[c * nlam + r];
+            }
+        }
+    }
+    __syncthreads();
+    for (int sidx = threadIdx.x; sidx < nseries; sidx += blockDim.x) {
+        double w[kMaxLam];
+        for (int r = 0; r < nlam; ++r) w[r] = y[(size_t)sidx * nlam + r];
+        for (int c = 0; c < nc; ++c) {
+            double dot = 0.0;
+            for (int r = c; r < nlam; ++r) dot += V[c * nlam + r] * w[r];
+            dot *= beta[c];
+            for (int r = c; r < nlam; ++r) w[r] -= dot * V[c * nlam + r];
+        }
+        double cf[kMaxDeg + 1];
+        for (int c = nc - 1; c >= 0; --c) {
+            double t = w[c];
+            for (int c2 = c + 1; c2 < nc; ++c2) t -= V[c2 * nlam + c] * cf[c2];
+            cf[c] = t / rdiag[c];
+        }
+        for (int c = 0; c < nc; ++c) coef[(size_t)sidx * nc + c] = cf[c];
+    }
+}
+
+// ---------------------------------------------------------------- drivers
+int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host, bool tt, bool mu,
+                      cudaStream_t s) {
+    if (tt) {
+        // gamma = alpha_tt per draw (slot PSFR_DRAW_ALPHA_TT), Moffat power 2
+        double* two = c->d_misc + kMiscTwo;   // holds the constant 2.0
+        const double h2 = 2.0;
+        PSFR_CUDA(c, cudaMemcpyAsync(two, &h2, sizeof(double), cudaMemcpyHostToDevice, s));
+        moffat_kernels_kernel<<<ndraw, 256, 0, s>>>(c->d_misc + misc_alpha_tt(c->max_planes), two, 0, c->d_kern_tt);
+        PSFR_LAUNCH_CHECK(c);
+    }
+    if (mu) {
+        // muse_intrinsic_psf (psfrec.py:1160-1168, np.polyval = Horner) and alpha = fwhm/0.2/(2 sqrt(2^(1/beta)-1)) (:923-924)
+        static const double pol_beta[6] = {-0.83704697, 1.1337153, 0.0609222, -1.35581762, 1.15237178, 2.2106042};
+        static const double pol_fwhm[6] = {0.60467385, -1.58905792, 1.75293264, -1.0368302, 0.21487023, 0.34851139};
+        double* h = static_cast<double*>(c->h_pinned);
+        for (int l = 0; l < nlam; ++l) {
+            const double lb = (10 * lambda_nm_host[l] - 4750) / (9350 - 4750);
+            double fw = 0.0, be = 0.0;
+            for (int k = 0; k < 6; ++k) {
+                fw = fw * lb + pol_fwhm[k];
+                be = be * lb + pol_beta[k];
+            }
+            fw = fw / 0.2;
+            h[l] = fw / (2 * sqrt(pow(2.0, 1. / be) - 1));
+            h[nlam + l] = be;
+        }
+        double* d = c->d_misc + kMiscMuse;    // gamma[nlam], beta[nlam]
+        PSFR_CUDA(c, cudaMemcpyAsync(d, h, 2 * nlam * sizeof(double), cudaMemcpyHostToDevice, s));
+        PSFR_CUDA(c, cudaStreamSynchronize(s));   // pinned bounce buffer is reused by the caller
+        moffat_kernels_kernel<<<nlam, 256, 0, s>>>(d, d + nlam, 1, c->d_kern_mu);
+        PSFR_LAUNCH_CHECK(c);
+    }
+    return PSFR_OK;
+}
+
+int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s) {
+    const size_t smem = (size_t)(kNS * kNS + 32) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        PSFR_CUDA(c, cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    resample_kernel<<<nimg, 256, smem, s>>>(c->d_samp, c->d_frac, nlam, cube_dev);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s) {
+    const size_t smem = (size_t)(2 * kImg + kKP * kKW) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        PSFR_CUDA(c, cudaFuncSetAttribute(convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    convolve_kernel<<<ndraw * nlam, 256, smem, s>>>(in_dev, c->d_kern_tt, c->d_kern_mu, nlam, out_dev);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s) {
+    const size_t smem = (size_t)(ny * nx + 4 * kNSUM + nx) * sizeof(double);
+    if (smem > 48 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+            PSFR_CUDA(c, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr = true;
+        }
+        if (smem > 200 * 1024) return set_error(c, PSFR_E_UNSUPPORTED, "image %dx%d too large for the fitter", ny, nx);
+    }
+    fit_kernel<<<nimg, kFitThreads, smem, s>>>(img_dev, ny, nx, fit_dev);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+int run_mean(Ctx* c, int ncube, int plane_elems, const double* cubes_dev, double* out_dev, cudaStream_t s) {
+    mean_kernel<<<(plane_elems + 255) / 256, 256, 0, s>>>(cubes_dev, ncube, (size_t)plane_elems, out_dev);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+int run_polyfit(Ctx* c, int nseries, int nlam, int deg, const double* lb_dev, const double* y_dev,
+                double* coef_dev, cudaStream_t s) {
+    if (nlam > kMaxLam || deg > kMaxDeg || deg + 1 > nlam)
+        return set_error(c, PSFR_E_UNSUPPORTED, "polyfit limits: nlam <= %d, deg <= %d", kMaxLam, kMaxDeg);
+    polyfit_kernel<<<1, 128, 0, s>>>(lb_dev, nlam, deg, nseries, y_dev, coef_dev);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
+}
+
+}  // namespace psfr

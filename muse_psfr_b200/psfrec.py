@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's ``muse_psfr/psfrec.py`` for the PSF-reconstruction
+hot path: same function names, argument meaning and error behaviour, computed by the
+sm_100a CUDA library behind the C ABI of ``include/psfr.h``.
+
+Only scalar bookkeeping happens here (per-draw constants such as r0, the 80x80
+frequency tables whose 1-ulp rounding the reference's cut-off masks depend on, result
+packaging).  Every array-sized computation runs on the GPU; there is no CPU fallback.
+"""
+import logging
+import os
+from math import gamma
+
+import numpy as np
+
+from . import _lib
+from ._lib import PsfrError
+
+logger = logging.getLogger('muse_psfr.psfrec')   # the reference's logger name (tests assert on it)
+
+MIN_L0 = 8    # psfrec.py:30-31
+MAX_L0 = 30
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_WIND_DIR = np.array([0.628163, -0.326497])      # psfrec.py:66
+_DIM = 1280                                      # psfrec.py:955
+_CONTEXTS = {}
+_DEFAULT_DEVICE = [None]
+
+
+# --------------------------------------------------------------------------- contexts
+def set_device(device):
+    """Select the GPU used by the module-level functions (default: LOCAL_RANK or 0)."""
+    _DEFAULT_DEVICE[0] = int(device)
+
+
+def _device():
+    if _DEFAULT_DEVICE[0] is None:
+        _DEFAULT_DEVICE[0] = int(os.environ.get('LOCAL_RANK', '0'))
+    return _DEFAULT_DEVICE[0]
+
+
+def get_context(max_planes=16, max_lambda=35, device=None):
+    """Context cache: one context per device, grown when a call needs more capacity."""
+    device = _device() if device is None else int(device)
+    ctx = _CONTEXTS.get(device)
+    if ctx is None or ctx.max_planes < max_planes or ctx.max_lambda < max_lambda:
+        if ctx is not None:
+            max_planes = max(max_planes, ctx.max_planes)
+            max_lambda = max(max_lambda, ctx.max_lambda)
+            ctx.close()
+        ctx = _lib.Context(device=device, dim=_DIM, max_planes=max_planes, max_lambda=max_lambda)
+        f, f_x, f_y = ao_frequency_tables()
+        ctx.set_geometry(f, f_x, f_y)
+        _CONTEXTS[device] = ctx
+    return ctx
+
+
+def release_contexts():
+    for ctx in _CONTEXTS.values():
+        ctx.close()
+    _CONTEXTS.clear()
+
+
+# --------------------------------------------------------------------------- scalar helpers
+def seeing2r01(seeing, lbda, zenith):
+    """seeing @ 0.5 microns, lambda in microns (psfrec.py:183-187)."""
+    r00p5 = 0.976 * 0.5 / seeing / 4.85
+    return r00p5 * (lbda * 2) ** (6 / 5) * np.cos(np.deg2rad(zenith)) ** (3 / 5)
+
+
+def direction_perf(npts, field_size=60, plot=False, lgs=None, ngs=None, ax=None):
+    """Grid of directions where the PSF is estimated (psfrec.py:154-180).  The plotting
+    branch of the reference (matplotlib) is outside the hot path and not provided."""
+    if plot:
+        raise NotImplementedError('plotting is outside the B200 hot path')
+    x, y = (np.mgrid[:npts, :npts] - npts // 2) * field_size / 2
+    return np.array([x, y]).reshape(2, -1)
+
+
+def pupil_mask(radius, width, oc=0, inverse=False):
+    """Annular pupil (psfrec.py:190-203); host helper kept for API parity - the library
+    builds its own pupil and telescope OTF on the device."""
+    center = (width - 1) / 2
+    x, y = np.ogrid[:int(width), :int(width)]
+    rho = np.hypot(x - center, y - center) / radius
+    mask = (rho < 1) & (rho >= oc)
+    return (~mask if inverse else mask).astype(int)
+
+
+def ao_frequency_tables(dimall=80, step=8. / 40):
+    """f, f_x, f_y of the AO zone, formed exactly as psfrec.py:548-554 and 241-242."""
+    fx = np.fft.fftfreq(int(dimall), step)[:, np.newaxis]
+    fy = fx.T
+    f = np.sqrt(fx ** 2 + fy ** 2)
+    with np.errstate(all='ignore'):
+        arg_f = fy / fx
+    arg_f[0, 0] = 0
+    arg_f = np.arctan(arg_f)
+    return f, f * np.cos(arg_f), f * np.sin(arg_f)
+
+
+def _lgs_positions(three_lgs_mode):
+    if three_lgs_mode:
+        poslgs = np.array([[1, 1], [-1, -1], [-1, 1]], dtype=float).T
+    else:
+        poslgs = np.array([[1, 1], [-1, -1], [-1, 1], [1, -1]], dtype=float).T
+    return poslgs * 63.          # psfrec.py:83-93
+
+
+_COEFF = [None]
+
+
+def _coeff_hl(L0):
+    """coeffHL(L0) from the reference's coeffL0 calibration table (psfrec.py:895-897)."""
+    if _COEFF[0] is None:
+        tab = np.loadtxt(os.path.join(_HERE, 'data', 'coeffL0.txt'), dtype=np.float32)
+        _COEFF[0] = (np.arange(1, tab.size + 1, dtype=np.float32), tab)
+    return np.interp(L0, *_COEFF[0])
+
+
+def tiptilt_alpha(seeing, GL, L0):
+    """Moffat alpha [px] of the residual tip-tilt kernel, beta = 2 (psfrec.py:879-905)."""
+    beta_tt = 2
+    seeingHL = seeing * (1 - GL) ** (3. / 5.)
+    r0HL = 0.976 * 0.5 / seeingHL / 4.85
+    coeffHL = _coeff_hl(L0)
+    pixscale = 0.2
+    fwhmTTopt = (np.sqrt(coeffHL * 0.97 * 6.88 * (.5 * 1.e-6 / (2. * np.pi)) ** 2 *
+                         8 ** (-1 / 3.) * r0HL ** (-5 / 3.)) / (4.85 * 1.e-6) * 2.35 / pixscale)
+    return fwhmTTopt / (2 * np.sqrt(2 ** (1. / beta_tt) - 1))
+
+
+def draw_record(Cn2, h, seeing, L0, zenith=0., alpha_tt=1.0):
+    """Per-draw constants of simul_psd_wfm / dsp4muse / psd_fit, evaluated with the
+    reference's own scalar expressions (psfrec.py:57-66, 108, 569-571, 594, 622-625)."""
+    Cn2 = np.array(Cn2, dtype=float)
+    Cn2 = Cn2 / Cn2.sum()
+    h_arr = np.array(h)
+    if h_arr.ndim != 1 or h_arr.size != Cn2.size:
+        raise ValueError('Cn2 and h must be 1-D sequences of the same length')
+    if h_arr.size > 2:
+        # the reference's wind directions are a hard-coded 2-vector (psfrec.py:66, 594)
+        raise ValueError('operands could not be broadcast together: at most 2 layers are supported')
+    vent = np.full_like(h_arr, 12.5)              # integer h -> 12 m/s, as the reference
+    arg_v = _WIND_DIR[:h_arr.size]
+    wind = np.stack([vent * np.cos(arg_v), vent * np.sin(arg_v)])
+    r0ref = seeing2r01(seeing, 0.5, zenith)
+    rec = np.zeros(_lib.DRAW_NPAR)
+    rec[_lib.DRAW_R0] = r0ref
+    rec[_lib.DRAW_L0] = L0
+    cst = ((gamma(11 / 6) ** 2 / (2 * np.pi ** (11 / 3))) * (24 * gamma(6 / 5) / 5) ** (5 / 6))
+    rec[_lib.DRAW_FITC] = cst * r0ref ** (-5 / 3)
+    for l in range(h_arr.size):
+        rec[_lib.DRAW_CPHI_0 + l] = 0.0229 * (Cn2[l] ** (-3 / 5) * r0ref) ** (-5 / 3)
+        rec[_lib.DRAW_H_0 + l] = float(h_arr[l])
+        rec[_lib.DRAW_WX_0 + 2 * l] = wind[0, l]
+        rec[_lib.DRAW_WY_0 + 2 * l] = wind[1, l]
+    rec[_lib.DRAW_ALPHA_TT] = alpha_tt
+    rec[_lib.DRAW_NLAYERS] = h_arr.size
+    return rec
+
+
+def draw_records(seeing, GL, L0, h=(100, 10000)):
+    """Vectorised ``draw_record`` for compute_psf's two-layer profile Cn2 = [GL, 1 - GL]
+    (psfrec.py:953); ``h`` is one pair or an array [ndraw, 2].  Same expressions as the
+    scalar version evaluated with numpy's array kernels, which may differ from libm's
+    scalar pow() by a few ulp (measured <= 3 ulp on the pow chains)."""
+    seeing, GL, L0 = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (seeing, GL, L0))
+    nd = seeing.size
+    h_arr = np.array(h)
+    if h_arr.shape[-1] != 2 or h_arr.ndim > 2:
+        raise ValueError('operands could not be broadcast together: h must hold 2 layer altitudes')
+    vent = np.full_like(h_arr, 12.5)             # integer altitudes -> 12 m/s, as the reference
+    wx, wy = vent * np.cos(_WIND_DIR), vent * np.sin(_WIND_DIR)
+    cn2 = np.stack([GL, 1 - GL], axis=1)
+    cn2 = cn2 / cn2.sum(axis=1)[:, None]
+    r0ref = seeing2r01(seeing, 0.5, 0.)
+    cst = ((gamma(11 / 6) ** 2 / (2 * np.pi ** (11 / 3))) * (24 * gamma(6 / 5) / 5) ** (5 / 6))
+    recs = np.zeros((nd, _lib.DRAW_NPAR))
+    recs[:, _lib.DRAW_R0] = r0ref
+    recs[:, _lib.DRAW_L0] = L0
+    recs[:, _lib.DRAW_FITC] = cst * r0ref ** (-5 / 3)
+    for l in range(2):
+        recs[:, _lib.DRAW_CPHI_0 + l] = 0.0229 * (cn2[:, l] ** (-3 / 5) * r0ref) ** (-5 / 3)
+        recs[:, _lib.DRAW_H_0 + l] = h_arr[..., l]
+        recs[:, _lib.DRAW_WX_0 + 2 * l] = wx[..., l]
+        recs[:, _lib.DRAW_WY_0 + 2 * l] = wy[..., l]
+    recs[:, _lib.DRAW_ALPHA_TT] = tiptilt_alpha(seeing, GL, L0)
+    recs[:, _lib.DRAW_NLAYERS] = 2
+    return recs
+
+
+# --------------------------------------------------------------------------- result table
+class FitTable:
+    """Column store with the columns of the reference's ``fit_psf_cube`` table
+    (psfrec.py:866-870).  ``to_astropy()`` converts when astropy is installed."""
+
+    def __init__(self, columns, meta=None):
+        self._cols = dict(columns)
+        self.meta = dict(meta or {})
+
+    @property
+    def colnames(self):
+        return list(self._cols)
+
+    def __len__(self):
+        return len(next(iter(self._cols.values())))
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self._cols[key]
+        if isinstance(key, (int, np.integer)):
+            return {k: v[key] for k, v in self._cols.items()}
+        return FitTable({k: v[key] for k, v in self._cols.items()}, self.meta)
+
+    def __setitem__(self, key, value):
+        n = len(self) if self._cols else None
+        arr = np.asarray(value)
+        self._cols[key] = np.full(n, value) if arr.ndim == 0 and n is not None else arr
+
+    def to_astropy(self):
+        from astropy.table import Table
+        return Table(self._cols, meta=self.meta)
+
+    @staticmethod
+    def vstack(tables):
+        names = tables[0].colnames
+        return FitTable({k: np.concatenate([np.atleast_1d(t[k]) for t in tables]) for k in names},
+                        tables[0].meta)
+
+
+def _table_from_fit(lbda, fit, pixscale=0.2):
+    fwhm = fit[:, _lib.FIT_FWHM] * pixscale
+    efw = fit[:, _lib.FIT_ERR_FWHM] * pixscale
+    return FitTable({
+        'lbda': np.asarray(lbda, dtype=float),
+        'center': fit[:, [_lib.FIT_Y0, _lib.FIT_X0]].copy(),
+        'flux': fit[:, _lib.FIT_FLUX].copy(),
+        'fwhm': np.stack([fwhm, fwhm], axis=1),
+        'n': fit[:, _lib.FIT_N].copy(),
+        'peak': fit[:, _lib.FIT_PEAK].copy(),
+        'err_center': fit[:, [_lib.FIT_ERR_Y0, _lib.FIT_ERR_X0]].copy(),
+        'err_flux': np.full(len(fit), np.nan),
+        'err_fwhm': np.stack([efw, efw], axis=1),
+        'err_n': fit[:, _lib.FIT_ERR_N].copy(),
+        'err_peak': fit[:, _lib.FIT_ERR_PEAK].copy(),
+    })
+
+
+# --------------------------------------------------------------------------- reference API
+def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., plot=False, npsflin=1, dim=1280,
+                  three_lgs_mode=False, verbose=True):
+    """Residual-phase PSD per field direction, [npsflin**2, dim, dim] in nm^2
+    (psfrec.py:36-151), synthesised on the GPU."""
+    if dim != _DIM:
+        raise NotImplementedError('this build supports dim=%d only' % _DIM)
+    if three_lgs_mode and verbose:
+        logger.info('Using three lasers mode')
+    rec = draw_record(Cn2, h, seeing, L0, zenith)
+    dirs = direction_perf(npsflin)
+    ctx = get_context(max_planes=max(16, dirs.shape[1]))
+    out = np.empty((dirs.shape[1], dim, dim))
+    ctx.psd(rec[None], dirs, _lgs_positions(three_lgs_mode), out=out)
+    return out
+
+
+def _standard_pupil_ok(pup, dim):
+    return pup is None or (np.shape(pup) == (dim // 2, dim // 2))
+
+
+def psd_to_psf(psd, pup, D, lbda, phase_static=None, samp=None, FoV=None, return_all=False):
+    """PSF from a residual-phase PSD (psfrec.py:689-807).  Only the branch the reference
+    itself exercises is provided: MUSE pupil of dim/2 pixels, D = 8 m,
+    samp = 2, FoV equal to the numerical field, no static phase."""
+    psd = np.ascontiguousarray(psd, dtype=np.float64)
+    dim = psd.shape[0]
+    if psd.ndim != 2 or dim != _DIM or psd.shape[1] != dim:
+        raise NotImplementedError('psd must be a %dx%d array' % (_DIM, _DIM))
+    if phase_static is not None or return_all:
+        raise NotImplementedError('static phase / return_all are not on the hot path')
+    if samp is not None and samp != 2:
+        raise NotImplementedError("FIXME: use gridddata or spline ?")   # the reference fails here too (:640)
+    if D != 8 or not _standard_pupil_ok(pup, dim):
+        raise NotImplementedError('only the MUSE pupil (D=8, dim/2 pixels, oc=0.14) is supported')
+    if pup is not None and not np.array_equal(np.asarray(pup) != 0, pupil_mask(dim / 4, dim / 2, oc=0.14) != 0):
+        raise NotImplementedError('only the MUSE pupil (D=8, dim/2 pixels, oc=0.14) is supported')
+    FoVnum = (lbda / (2 * D)) * dim / (4.85 * 1.e-6)
+    if FoV is not None and not np.allclose(FoV, FoVnum):
+        raise NotImplementedError("FIXME: use gridddata or spline ?")
+    ctx = get_context()
+    ctx.load_psd(psd, 1)
+    ctx.structure_function(1)
+    out = np.empty((dim, dim))
+    ctx.psd_to_psf(0, lbda, out)
+    return out
+
+
+def psf_muse(psd, lambdamuse):
+    """40x40 PSFs at 0.2 arcsec/pixel for each wavelength [nm] (psfrec.py:644-686)."""
+    psd = np.ascontiguousarray(psd, dtype=np.float64)
+    lam = np.atleast_1d(np.asarray(lambdamuse, dtype=float))
+    if psd.ndim == 2:
+        psd = psd[None]
+    if psd.ndim != 3 or psd.shape[1:] != (_DIM, _DIM):
+        raise NotImplementedError('psd must be [ndir, %d, %d]' % (_DIM, _DIM))
+    ndir = psd.shape[0]
+    ctx = get_context(max_planes=max(16, ndir), max_lambda=max(35, lam.size))
+    ctx.load_psd(psd, ndir)
+    ctx.structure_function(ndir)
+    out = np.empty((lam.size, _lib.PSF_DIM, _lib.PSF_DIM))
+    try:
+        ctx.psf_cube(1, ndir, lam, out)
+    except PsfrError as exc:
+        if exc.code == _lib.E_UNSUPPORTED:
+            raise ValueError(str(exc))      # the reference raises ValueError from interpn / crop here
+        raise
+    return out
+
+
+def muse_intrinsic_psf(lbda):
+    """MUSE PSF polynomial approximation (psfrec.py:1144-1171): fwhm, beta, fwhm_std, beta_std."""
+    pol_beta = [-0.83704697, 1.1337153, 0.0609222, -1.35581762, 1.15237178, 2.2106042]
+    pol_fwhm = [0.60467385, -1.58905792, 1.75293264, -1.0368302, 0.21487023, 0.34851139]
+    pol_beta_std = [0.18187424, -0.17841793, 0.30962616]
+    pol_fwhm_std = [0.00707504, -0.0303464, 0.04596354]
+    lb = (10 * np.asarray(lbda, dtype=float) - 4750) / (9350 - 4750)
+    return (np.polyval(pol_fwhm, lb), np.polyval(pol_beta, lb),
+            np.polyval(pol_fwhm_std, lb), np.polyval(pol_beta_std, lb))
+
+
+def convolve_final_psf(lbda, seeing, GL, L0, psf):
+    """Convolve with the tip-tilt and MUSE Moffat kernels (psfrec.py:874-930)."""
+    lam = np.atleast_1d(np.asarray(lbda, dtype=float))
+    psf = np.ascontiguousarray(psf, dtype=np.float64)
+    if psf.shape != (lam.size, _lib.PSF_DIM, _lib.PSF_DIM):
+        raise NotImplementedError('psf must be [nl, 40, 40]')
+    ctx = get_context(max_lambda=max(35, lam.size))
+    out = np.empty_like(psf)
+    ctx.convolve(1, lam, [tiptilt_alpha(seeing, GL, L0)], psf, out)
+    return out
+
+
+def fit_psf_cube(lbda, psfcube):
+    """Fit a Moffat PSF on each wavelength plane (psfrec.py:861-871).  ``psfcube`` is an
+    array [nl, ny, nx] (or anything with a ``.data`` array, like an mpdaf Cube)."""
+    data = getattr(psfcube, 'data', psfcube)
+    data = np.ascontiguousarray(np.ma.getdata(data), dtype=np.float64)
+    lam = np.atleast_1d(np.asarray(lbda, dtype=float))
+    nimg, ny, nx = data.shape
+    ctx = get_context()
+    fit = np.empty((nimg, _lib.FIT_NPAR))
+    ctx.moffat_fit(nimg, ny, nx, data, fit)
+    return _table_from_fit(lam, fit)
+
+
+def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, verbose=True):
+    """Reconstruct a PSF from seeing, GL and L0 (psfrec.py:933-978): returns (table, psf)."""
+    if verbose:
+        logger.info('Compute PSF with seeing=%.2f GL=%.2f L0=%.2f', seeing, GL, L0)
+        if three_lgs_mode:
+            logger.info('Using three lasers mode')
+    lam = np.atleast_1d(np.asarray(lbda, dtype=float))
+    fit, cube = compute_psf_batch(lam, [seeing], [GL], [L0], npsflin=npsflin, h=h,
+                                  three_lgs_mode=three_lgs_mode)
+    res = _table_from_fit(lam, fit[0])
+    res.meta.update({'SEEING': seeing, 'GL': GL, 'L0': L0})
+    res['SEEING'] = seeing
+    res['GL'] = GL
+    res['L0'] = L0
+    return res, cube[0]
+
+
+reconstruct_psf = compute_psf   # pre-1.0 name used by BASELINE.json's north_star (CHANGELOG:6)
+
+
+def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False,
+                      out_cube=None, out_fit=None, want_cube=True, device=None, max_planes=64, stream=None):
+    """Batched ``compute_psf``: one fused device pipeline for many (seeing, GL, L0[, h]) draws.
+
+    ``h`` is one (h0, h1) pair or an array [ndraw, 2].  Returns (fit [ndraw, nl, FIT_NPAR],
+    cube [ndraw, nl, 40, 40]); ``out_cube`` / ``out_fit`` may be preallocated numpy arrays or
+    torch tensors (host-pinned or device) used as plain buffers."""
+    lam = np.atleast_1d(np.asarray(lbda, dtype=float))
+    seeing, GL, L0 = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (seeing, GL, L0))
+    nd = seeing.size
+    if nd <= 64:
+        # scalar expressions, bit-identical to the reference's own scalars
+        h_arr = np.array(h)
+        recs = np.stack([draw_record([GL[i], 1 - GL[i]], h_arr[i] if h_arr.ndim == 2 else h_arr, seeing[i],
+                                     L0[i], 0., alpha_tt=tiptilt_alpha(seeing[i], GL[i], L0[i]))
+                         for i in range(nd)])
+    else:
+        recs = draw_records(seeing, GL, L0, h)
+    dirs = direction_perf(npsflin)
+    ctx = get_context(max_planes=max(dirs.shape[1], min(max_planes, nd * dirs.shape[1])),
+                      max_lambda=max(35, lam.size), device=device)
+    if out_fit is None:
+        out_fit = np.empty((nd, lam.size, _lib.FIT_NPAR))
+    if out_cube is None and want_cube:
+        out_cube = np.empty((nd, lam.size, _lib.PSF_DIM, _lib.PSF_DIM))
+    try:
+        ctx.compute_batch(recs, dirs, _lgs_positions(three_lgs_mode), lam, out_cube=out_cube,
+                          out_fit=out_fit, stream=stream)
+    except PsfrError as exc:
+        if exc.code == _lib.E_UNSUPPORTED:
+            raise ValueError(str(exc))
+        raise
+    return out_fit, out_cube
+
+
+def _norm_lbda(lbda, lb1, lb2):
+    return (lbda - lb1) / (lb2 - lb1) - 0.5
+
+
+def fit_psf_with_polynom(lbda, fwhm, beta, deg=(5, 5), output=0):
+    """Fit MUSE PSF fwhm and beta with polynomials in the normalised wavelength
+    (psfrec.py:1174-1210); least squares solved on the device (Householder QR)."""
+    lbda = np.asarray(lbda, dtype=float)
+    ctx = get_context()
+    if deg[0] == deg[1]:
+        coef = ctx.polyfit(lbda, deg[0], np.stack([np.asarray(fwhm, float), np.asarray(beta, float)]))
+        fwhm_pol, beta_pol = coef[0], coef[1]
+    else:
+        fwhm_pol = ctx.polyfit(lbda, deg[0], np.asarray(fwhm, float))[0]
+        beta_pol = ctx.polyfit(lbda, deg[1], np.asarray(beta, float))[0]
+    res = dict(fwhm_pol=fwhm_pol, beta_pol=beta_pol, lbda=lbda, lbda_lim=(475, 935))
+    if output > 0:
+        lbda_fit = np.linspace(475, 935, 50)
+        lbf = _norm_lbda(lbda_fit, 475, 935)
+        res['lbda_fit'] = lbda_fit
+        res['fwhm_fit'] = np.polyval(fwhm_pol, lbf)
+        res['beta_fit'] = np.polyval(beta_pol, lbf)
+    return res

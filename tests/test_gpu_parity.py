@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path (through the C ABI and the reference-shaped Python
+functions) against the CPU oracle on the same inputs and against the committed fixtures
+generated from the reference's own code.
+
+Tolerances (BASELINE.json): PSF images relative 1e-9 in FP64; fitted FWHM / beta relative 1e-5.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import psfr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LBDA35 = np.linspace(490, 930, 35)
+PSF_RTOL = 1e-9      # north_star: PSF images to relative 1e-9
+FIT_RTOL = 1e-5      # north_star: FWHM / beta to relative 1e-5
+
+
+@pytest.fixture(scope='module')
+def psfrec():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from muse_psfr_b200 import psfrec as mod
+    mod.set_device(0)
+    yield mod
+    mod.release_contexts()
+
+
+@pytest.fixture(scope='module')
+def psd1():
+    return orc.simul_psd_wfm([0.7, 0.3], (100, 10000), 1.0, 25.)
+
+
+def rel_to_peak(got, ref):
+    return np.abs(np.asarray(got) - np.asarray(ref)).max() / np.abs(ref).max()
+
+
+def assert_image_close(got, ref, rtol=PSF_RTOL):
+    """Relative 1e-9: every pixel above 1e-6 of the peak agrees to rtol pointwise, and the
+    whole image agrees to rtol of the peak."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    assert rel_to_peak(got, ref) < rtol
+    sig = np.abs(ref) > 1e-6 * np.abs(ref).max()
+    assert_allclose(got[sig], ref[sig], rtol=rtol, atol=0)
+
+
+# ---------------------------------------------------------------- init constants
+def test_telescope_otf(psfrec):
+    t = psfrec.get_context().get_otf()
+    ref = orc.telescope_otf(orc.pupil_mask(320, 640, 0.14), 1280)
+    assert rel_to_peak(t[:641], ref[:641]) < 1e-13
+    assert np.all(t[641] == 0)
+    assert_allclose(t[640, 640] * 1280 ** 2, 1.0, rtol=1e-15)
+    # exact zeros outside the pupil-autocorrelation support (disc of radius N/2)
+    yy, xx = np.ogrid[:641, :1280]
+    assert np.all(t[:641][np.hypot(yy - 640, xx - 640) > 641] == 0)
+
+
+# ---------------------------------------------------------------- PSD synthesis (a1-a7)
+@pytest.mark.parametrize('args,kw', [
+    (([0.7, 0.3], (100, 10000), 1.0, 25.), dict(npsflin=1)),
+    (([0.7, 0.3], (100, 10000), 1.0, 25.), dict(npsflin=3, three_lgs_mode=True)),
+    (([0.55, 0.45], (150.5, 12000.), 0.63, 12.5), dict(npsflin=2)),
+    (([1.0], (300.,), 1.4, 9.5), dict(npsflin=1)),
+])
+def test_simul_psd_wfm(psfrec, args, kw):
+    got = psfrec.simul_psd_wfm(*args, verbose=False, **kw)
+    ref = orc.simul_psd_wfm(*args, **kw)
+    assert got.shape == ref.shape
+    assert np.array_equal(got == 0, ref == 0)            # cut-off masks bit-exact
+    assert_allclose(got, ref, rtol=1e-10, atol=0)
+    assert_allclose(got.sum(axis=(1, 2)), ref.sum(axis=(1, 2)), rtol=1e-12)
+
+
+def test_psd_golden_config3(psfrec, golden):
+    g = golden('ref_config3')
+    got = psfrec.simul_psd_wfm([0.7, 0.3], (100, 10000), 1.0, 25., npsflin=3, three_lgs_mode=True, verbose=False)
+    assert_allclose(got[:, 600:680, 600:680], g['psd_aozone'], rtol=1e-10)
+    assert_allclose(got.sum(axis=(1, 2)), g['psd_sum'], rtol=1e-12)
+
+
+def test_three_layers_rejected(psfrec):
+    with pytest.raises(ValueError):
+        psfrec.simul_psd_wfm([0.5, 0.3, 0.2], (100, 5000, 10000), 1.0, 25.)
+
+
+# ---------------------------------------------------------------- structure function / psd_to_psf (a8)
+def test_structure_function(psfrec, psd1):
+    ctx = psfrec.get_context()
+    ctx.load_psd(np.ascontiguousarray(psd1[0]), 1)
+    ctx.structure_function(1)
+    d = ctx.get_structure_function(0)
+    ref = orc.structure_function_unit(psd1[0])
+    assert rel_to_peak(d[:641], ref.T[:641]) < 1e-13
+    assert d[640, 640] == 0.0 and np.all(d[641] == 0)
+
+
+@pytest.mark.parametrize('lb', [490e-9, 710e-9, 930e-9])
+def test_psd_to_psf_full_grid(psfrec, psd1, golden, lb):
+    pup = orc.pupil_mask(320, 640, 0.14)
+    got = psfrec.psd_to_psf(psd1[0], pup, 8, lb, samp=2)
+    ref = orc.psd_to_psf(psd1[0], pup, 8, lb)
+    assert_image_close(got, ref)
+    assert_allclose(got.sum(), 1.0, rtol=1e-12)
+    g = golden('ref_config1')
+    name = 'psf%d' % round(lb * 1e9)
+    assert_allclose(got[640 - 48:640 + 48, 640 - 48:640 + 48], g[name + '_centre'], rtol=PSF_RTOL)
+    assert rel_to_peak(got[::16, ::16], g[name + '_lattice']) < PSF_RTOL
+
+
+def test_psd_to_psf_dead_branches(psfrec, psd1):
+    pup = orc.pupil_mask(320, 640, 0.14)
+    with pytest.raises(NotImplementedError):
+        psfrec.psd_to_psf(psd1[0], pup, 8, 500e-9, samp=3)
+    with pytest.raises(NotImplementedError):
+        psfrec.psd_to_psf(psd1[0], pup, 8, 500e-9, samp=2, FoV=10.)
+    with pytest.raises(NotImplementedError):
+        psfrec.psd_to_psf(psd1[0][:640, :640], pup[:320, :320], 8, 500e-9)
+
+
+# ---------------------------------------------------------------- psf_muse (a9)
+def test_psf_muse_config1_golden(psfrec, psd1, golden):
+    g = golden('ref_config1')
+    got = psfrec.psf_muse(psd1[0], LBDA35)
+    assert got.shape == (35, 40, 40)
+    for i in range(35):
+        assert_image_close(got[i], g['psf_muse'][i])
+    assert_allclose(got.sum(axis=(1, 2)), 1.0, rtol=1e-13)
+    assert_allclose(got[0].max(), 0.06878001975345309, rtol=1e-9)     # SURVEY 8c probes
+    assert_allclose(got[34].max(), 0.1438347394519584, rtol=1e-9)
+
+
+def test_psf_muse_nine_directions(psfrec, golden):
+    g = golden('ref_config3')
+    psd3 = orc.simul_psd_wfm([0.7, 0.3], (100, 10000), 1.0, 25., npsflin=3, three_lgs_mode=True)
+    got = psfrec.psf_muse(psd3, g['lbda'])
+    for i in range(len(g['lbda'])):
+        assert_image_close(got[i], g['psf_muse'][i])
+
+
+def test_psf_muse_pruned_equals_full_grid(psfrec, psd1):
+    """The pruned 80x80-sample transform against the full-grid PSF resampled on the host."""
+    from scipy.interpolate import interpn
+    lb = 611.0
+    full = psfrec.psd_to_psf(psd1[0], None, 8, lb * 1e-9)
+    npx = int(orc.npixc_of(lb)[0])
+    crop = full[640 - npx // 2:640 + npx // 2, 640 - npx // 2:640 + npx // 2].copy()
+    crop /= crop.sum()
+    np.maximum(crop, 0, out=crop)
+    pos = np.mgrid[:40, :40] * npx / 40
+    ref = interpn((np.arange(npx), np.arange(npx)), crop, pos.T).T
+    ref /= ref.sum()
+    got = psfrec.psf_muse(psd1[0], np.array([lb]))[0]
+    assert_image_close(got, ref, rtol=1e-11)
+
+
+def test_wavelength_below_grid_limit(psfrec, psd1):
+    with pytest.raises(ValueError):
+        psfrec.psf_muse(psd1[0], np.array([400.]))      # needs a 1552-pixel crop: reference fails too
+
+
+# ---------------------------------------------------------------- convolve + fit (a10, a11)
+def test_convolve_final_psf(psfrec, golden):
+    g, go = golden('ref_config1'), golden('oracle_config1')
+    got = psfrec.convolve_final_psf(LBDA35, 1.0, 0.7, 25., g['psf_muse'])
+    for i in range(35):
+        assert_image_close(got[i], go['conv'][i])
+    ref = orc.convolve_final_psf(LBDA35[[3]], 0.6, 0.45, 11., g['psf_muse'][[3]])
+    assert_image_close(psfrec.convolve_final_psf(LBDA35[[3]], 0.6, 0.45, 11., g['psf_muse'][[3]])[0], ref[0])
+
+
+def test_fit_psf_cube(psfrec, golden):
+    go = golden('oracle_config1')
+    tab = psfrec.fit_psf_cube(LBDA35, go['conv'])
+    assert_allclose(tab['fwhm'][:, 0], go['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(tab['n'], go['n'], rtol=FIT_RTOL)
+    assert_allclose(tab['center'], go['center'], atol=1e-5)
+    assert_allclose(tab['peak'], go['peak'], rtol=FIT_RTOL)
+    assert_allclose(tab['lbda'], LBDA35)
+
+
+def test_fit_exact_moffat_known_answer(psfrec):
+    """Idempotence: images that ARE Moffat profiles return their own parameters."""
+    p, q = np.mgrid[:40, :40].astype(float)
+    truth = [(0.07, 20.3, 19.6, 3.1, 2.4), (0.15, 19.5, 20.5, 2.2, 1.8), (0.02, 21.0, 18.2, 5.5, 3.5)]
+    imgs = np.stack([orc.moffat_model(np.array(v), p, q) for v in truth])
+    tab = psfrec.fit_psf_cube(np.arange(3.), imgs)
+    for k, v in enumerate(truth):
+        assert_allclose(tab['peak'][k], v[0], rtol=1e-9)
+        assert_allclose(tab['center'][k], v[1:3], rtol=1e-9)
+        assert_allclose(tab['n'][k], v[4], rtol=1e-8)
+        assert_allclose(tab['fwhm'][k, 0], 0.2 * v[3] * 2 * np.sqrt(2 ** (1 / v[4]) - 1), rtol=1e-8)
+
+
+def test_fit_non_square_image(psfrec):
+    p, q = np.mgrid[:32, :48].astype(float)
+    img = orc.moffat_model(np.array([1.0, 15.2, 25.1, 3.0, 2.5]), p, q)
+    tab = psfrec.fit_psf_cube([0.], img[None])
+    assert_allclose(tab['center'][0], [15.2, 25.1], rtol=1e-8)
+    assert_allclose(tab['n'][0], 2.5, rtol=1e-7)
+
+
+# ---------------------------------------------------------------- compute_psf end to end (a13)
+def test_compute_psf_config1(psfrec, golden):
+    go = golden('oracle_config1')
+    tab, cube = psfrec.compute_psf(LBDA35, 1.0, 0.7, 25., verbose=False)
+    for i in range(35):
+        assert_image_close(cube[i], go['conv'][i])
+    assert_allclose(tab['fwhm'][:, 0], go['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(tab['n'], go['n'], rtol=FIT_RTOL)
+    assert_allclose(tab['center'], 20, atol=1e-3)
+    assert tab.meta == {'SEEING': 1.0, 'GL': 0.7, 'L0': 25.}
+    assert_allclose(tab['L0'], 25.)
+
+
+def test_compute_psf_reference_known_answers(psfrec):
+    """test_psfrec.py:121-128 / 162-170."""
+    tab, _ = psfrec.reconstruct_psf(np.array([500., 700., 900.]), 1.0, 0.7, 25., verbose=False)
+    assert ['%.2f' % v for v in tab['fwhm'][:, 0]] == ['0.85', '0.73', '0.62']
+    assert ['%.2f' % v for v in tab['n']] == ['2.73', '2.55', '2.23']
+
+
+def test_compute_psf_config3(psfrec, golden):
+    """npsflin=3 with three lasers (test_psfrec.py:77-90: fwhm 0.86 at 502.9 nm)."""
+    o3 = golden('oracle_config3')
+    tab, cube = psfrec.compute_psf(o3['lbda'], 1.0, 0.7, 25., npsflin=3, three_lgs_mode=True, verbose=False)
+    for i in range(len(o3['lbda'])):
+        assert_image_close(cube[i], o3['conv'][i])
+    assert_allclose(tab['fwhm'][:, 0], o3['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(tab['n'], o3['n'], rtol=FIT_RTOL)
+
+
+def test_batch_config4_sample(psfrec, golden):
+    g4, o4 = golden('ref_config4_sample'), golden('oracle_config4_sample')
+    pick = g4['pick']
+    from muse_psfr_b200 import _lib
+    fit, cube = psfrec.compute_psf_batch(g4['lbda'], g4['seeing'][pick], g4['GL'][pick], g4['L0'][pick],
+                                         h=np.stack([g4['h0'][pick], g4['h1'][pick]], axis=1))
+    for k in range(len(pick)):
+        for i in range(len(g4['lbda'])):
+            assert_image_close(cube[k, i], o4['conv'][k, i])
+    assert_allclose(fit[:, :, _lib.FIT_FWHM] * 0.2, o4['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(fit[:, :, _lib.FIT_N], o4['n'], rtol=FIT_RTOL)
+    assert np.all(fit[:, :, _lib.FIT_ITER] > 0)
+
+
+def test_batch_is_independent_of_chunking(psfrec):
+    """Size-independent property at batch scale: a draw's result does not depend on which
+    other draws share its launch (chunk of 64 planes vs chunks of 7)."""
+    rng = np.random.default_rng(7)
+    nd = 100
+    s, g, l0 = rng.uniform(.4, 2, nd), rng.uniform(.3, .95, nd), rng.uniform(9, 29, nd)
+    h = np.stack([rng.uniform(50, 500, nd), rng.uniform(5000, 15000, nd)], 1)
+    lam = LBDA35[::6]
+    from muse_psfr_b200 import _lib
+    fit_a, cube_a = psfrec.compute_psf_batch(lam, s, g, l0, h=h, max_planes=64)
+    assert np.isfinite(cube_a).all() and np.all(fit_a[:, :, _lib.FIT_ITER] > 0)
+    psfrec.release_contexts()
+    ctx = psfrec.get_context(max_planes=7, max_lambda=35)
+    recs = psfrec.draw_records(s, g, l0, h)
+    fit_b = np.empty_like(fit_a)
+    cube_b = np.empty_like(cube_a)
+    ctx.compute_batch(recs, psfrec.direction_perf(1), psfrec._lgs_positions(False), lam, out_cube=cube_b, out_fit=fit_b)
+    assert np.array_equal(cube_a, cube_b)
+    assert np.array_equal(fit_a, fit_b)
+    psfrec.release_contexts()
+    # spot-check three draws against the oracle
+    for i in (0, 57, 99):
+        ref_fit, ref_cube = orc.compute_psf(lam[:2], s[i], g[i], l0[i], h=tuple(h[i]))
+        assert_image_close(cube_a[i, 0], ref_cube[0])
+        assert_allclose(fit_a[i, :2, _lib.FIT_FWHM] * 0.2, ref_fit['fwhm'], rtol=FIT_RTOL)
+        assert_allclose(fit_a[i, :2, _lib.FIT_N], ref_fit['n'], rtol=FIT_RTOL)
+
+
+# ---------------------------------------------------------------- mean + refit, polynomials (a12, a13)
+def test_mean_refit(psfrec, golden):
+    go = golden('oracle_config1')
+    from muse_psfr_b200 import _lib
+    cubes = np.ascontiguousarray(np.stack([go['conv'], go['conv'][::-1], 0.5 * go['conv']]))
+    mean = np.empty((35, 40, 40))
+    fit = np.empty((35, _lib.FIT_NPAR))
+    psfrec.get_context().mean_refit(3, 35, cubes, mean, fit)
+    assert_allclose(mean, np.mean(cubes, axis=0), rtol=1e-15)
+    ref = orc.fit_psf_cube(LBDA35[[0, 20]], np.mean(cubes, axis=0)[[0, 20]])
+    assert_allclose(fit[[0, 20], _lib.FIT_FWHM] * 0.2, ref['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(fit[[0, 20], _lib.FIT_N], ref['n'], rtol=FIT_RTOL)
+
+
+def test_fit_psf_with_polynom(psfrec, golden):
+    go = golden('oracle_config1')
+    pol = psfrec.fit_psf_with_polynom(LBDA35, go['fwhm'], go['n'], output=1)
+    assert_allclose(pol['fwhm_pol'], go['ref_fwhm_pol'], rtol=1e-8)
+    assert_allclose(pol['beta_pol'], go['ref_beta_pol'], rtol=1e-8)
+    assert_allclose(pol['fwhm_fit'], go['ref_fwhm_fit'], rtol=1e-10)
+    assert_allclose(pol['beta_fit'], go['ref_beta_fit'], rtol=1e-10)
+    assert pol['lbda_lim'] == (475, 935)
+    mixed = psfrec.fit_psf_with_polynom(LBDA35, go['fwhm'], go['n'], deg=(3, 4))
+    assert_allclose(mixed['fwhm_pol'], np.polyfit(orc.norm_lbda(LBDA35), go['fwhm'], 3), rtol=1e-9)
+    assert_allclose(mixed['beta_pol'], np.polyfit(orc.norm_lbda(LBDA35), go['n'], 4), rtol=1e-9)
+
+
+def test_kernels_were_launched(psfrec):
+    psfrec.compute_psf(np.array([600.]), 0.9, 0.6, 20., verbose=False)
+    ctx = psfrec.get_context()
+    assert ctx.kernel_launches() > 0
+    ms, n, psfs = ctx.last_hot_timing()
+    assert n == 1 and psfs == 1 and ms > 0

@@ -1,0 +1,85 @@
+// CPU emulation of the warp FFT in csrc/warp_fft.cuh: runs the same __host__ __device__
+// phase functions lane by lane and compares with a direct O(N^2) DFT.  Build + run:
+//   nvcc -O2 -I muse_psfr_b200/csrc tools/host_check.cu -o /tmp/host_check && /tmp/host_check
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "warp_fft.cuh"
+#include "fft_tables.h"
+using namespace psfr;
+
+template <int R3>
+int check() {
+    using G = FftGeom<R3>;
+    const int N = G::N;
+    std::vector<double2> tw1, tw2;
+    build_twiddles<R3>(tw1, tw2);
+    std::vector<double2> x(N);
+    srand(1);
+    for (auto& z : x) z = make_double2(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
+    std::vector<std::vector<double2>> v(32, std::vector<double2>(40));
+    std::vector<double> sm(G::XBUF);
+    for (int t = 0; t < 32; ++t)
+        for (int j = 0; j < 5; ++j)
+            for (int n1 = 0; n1 < 8; ++n1) v[t][j * 8 + n1] = x[n1 * (N / 8) + t + 32 * j];
+    for (int t = 0; t < 32; ++t) fft_pass1<R3>(v[t].data(), tw1.data(), t);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_x1_store<R3>(v[t].data(), sm.data(), t, c);
+        for (int t = 0; t < 32; ++t) fft_x1_load<R3>(v[t].data(), sm.data(), t, c);
+    }
+    for (int t = 0; t < 32; ++t) fft_pass2<R3>(v[t].data(), tw2.data(), t);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_x2_store<R3>(v[t].data(), sm.data(), t, c);
+        for (int t = 0; t < 32; ++t) fft_x2_load<R3>(v[t].data(), sm.data(), t, c);
+    }
+    for (int t = 0; t < 32; ++t) fft_pass3<R3>(v[t].data());
+    std::vector<double2> X(N);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_dump<R3>(v[t].data(), sm.data(), t, c);
+        for (int k = 0; k < N; ++k) comp_set(X[k], c, sm[nat_addr(k)]);
+    }
+    double maxerr = 0, maxref = 0;
+    for (int k = 0; k < N; k += 7) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            double2 w = unit_root((long long)n * k, N);
+            sr += (long double)x[n].x * w.x - (long double)x[n].y * w.y;
+            si += (long double)x[n].x * w.y + (long double)x[n].y * w.x;
+        }
+        double e = fabs((double)(sr - X[k].x)) + fabs((double)(si - X[k].y));
+        if (e > maxerr) maxerr = e;
+        double r = fabs((double)sr) + fabs((double)si);
+        if (r > maxref) maxref = r;
+    }
+    printf("N=%d max err %.3e (ref scale %.3e) rel %.3e\n", N, maxerr, maxref, maxerr / maxref);
+    return maxerr / maxref < 1e-14 ? 0 : 1;
+}
+
+int main() {
+    // small DFT sanity: dft_r3 for 5,10,20,40
+    int bad = 0;
+    {
+        double2 x[40], y[40];
+        for (int R : {5, 10, 20, 40}) {
+            for (int i = 0; i < R; ++i) x[i] = y[i] = make_double2(0.3 * i - 1, 0.1 * i * i - 2);
+            if (R == 5) dft_r3<5>(y);
+            if (R == 10) dft_r3<10>(y);
+            if (R == 20) dft_r3<20>(y);
+            if (R == 40) dft_r3<40>(y);
+            double me = 0;
+            for (int k = 0; k < R; ++k) {
+                double sr = 0, si = 0;
+                for (int n = 0; n < R; ++n) {
+                    double2 w = unit_root(n * k, R);
+                    sr += x[n].x * w.x - x[n].y * w.y;
+                    si += x[n].x * w.y + x[n].y * w.x;
+                }
+                me = fmax(me, fabs(sr - y[k].x) + fabs(si - y[k].y));
+            }
+            printf("dft_r3<%d> err %.3e\n", R, me);
+            if (me > 1e-11) bad = 1;
+        }
+    }
+    bad |= check<20>();
+    return bad;
+}
