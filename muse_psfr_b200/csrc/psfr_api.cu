@@ -93,20 +93,18 @@ static int small_to_host(Ctx* c, std::vector<double>& dst, const double* src, si
     return PSFR_OK;
 }
 
-static int upload_draws(Ctx* c, int ndraw, const double* draws, int ndir, const double* dirs, int ngs,
-                        const double* pos, cudaStream_t s) {
-    if (ndraw < 1 || ndir < 1 || ndraw * ndir > c->max_planes)
-        return set_error(c, PSFR_E_CAPACITY, "ndraw*ndir = %d exceeds max_planes = %d", ndraw * ndir, c->max_planes);
+// geometry of a call: directions and guide-star positions; validates the whole draw list once
+// (reference: ValueError for > 2 layers, psfrec.py:66,594).  One host sync at most.
+static int upload_geometry(Ctx* c, int ndraw, const double* draws, int ndir, const double* dirs, int ngs,
+                           const double* pos, cudaStream_t s) {
+    if (ndraw < 1 || ndir < 1) return set_error(c, PSFR_E_ARG, "ndraw=%d ndir=%d", ndraw, ndir);
     if (ngs < 1 || ngs > kMaxGS) return set_error(c, PSFR_E_ARG, "ngs=%d outside [1,%d]", ngs, kMaxGS);
     if (ndir > kMaxDir) return set_error(c, PSFR_E_ARG, "ndir=%d exceeds %d", ndir, kMaxDir);
     if (!c->geometry_set) return set_error(c, PSFR_E_STATE, "psfr_set_geometry has not been called");
-    int rc = to_device(c, c->d_draws, draws, (size_t)ndraw * PSFR_DRAW_NPAR * sizeof(double), s);
-    if (rc) return rc;
-    rc = to_device(c, c->d_misc + kMiscDirs, dirs, (size_t)2 * ndir * sizeof(double), s);
+    int rc = to_device(c, c->d_misc + kMiscDirs, dirs, (size_t)2 * ndir * sizeof(double), s);
     if (rc) return rc;
     rc = to_device(c, c->d_misc + kMiscPos, pos, (size_t)2 * ngs * sizeof(double), s);
     if (rc) return rc;
-    // validate the layer count (reference: ValueError for > 2 layers, psfrec.py:66,594)
     std::vector<double> h;
     rc = small_to_host(c, h, draws, (size_t)ndraw * PSFR_DRAW_NPAR, s);
     if (rc) return rc;
@@ -115,12 +113,18 @@ static int upload_draws(Ctx* c, int ndraw, const double* draws, int ndir, const 
         if (!(nl == 1.0 || nl == 2.0))
             return set_error(c, PSFR_E_UNSUPPORTED, "draw %d has %g layers; the reference supports 1 or 2", d, nl);
     }
-    // tip-tilt alphas next to the plane centres
-    std::vector<double> att(ndraw);
-    for (int d = 0; d < ndraw; ++d) att[d] = h[(size_t)d * PSFR_DRAW_NPAR + PSFR_DRAW_ALPHA_TT];
-    PSFR_CUDA(c, cudaMemcpyAsync(c->d_misc + misc_alpha_tt(c->max_planes), att.data(), ndraw * sizeof(double),
-                                 cudaMemcpyHostToDevice, s));
-    PSFR_CUDA(c, cudaStreamSynchronize(s));
+    return PSFR_OK;
+}
+
+// records of one chunk of draws -> d_draws, their tip-tilt alphas -> scratch; stream-ordered, no sync
+static int upload_draws(Ctx* c, int ndraw, const double* draws, int ndir, cudaStream_t s) {
+    if (ndraw < 1 || ndraw * ndir > c->max_planes)
+        return set_error(c, PSFR_E_CAPACITY, "ndraw*ndir = %d exceeds max_planes = %d", ndraw * ndir, c->max_planes);
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_draws, draws, (size_t)ndraw * PSFR_DRAW_NPAR * sizeof(double),
+                                 cudaMemcpyDefault, s));
+    PSFR_CUDA(c, cudaMemcpy2DAsync(c->d_misc + misc_alpha_tt(c->max_planes), sizeof(double),
+                                   c->d_draws + PSFR_DRAW_ALPHA_TT, PSFR_DRAW_NPAR * sizeof(double),
+                                   sizeof(double), ndraw, cudaMemcpyDeviceToDevice, s));
     return PSFR_OK;
 }
 
@@ -257,8 +261,9 @@ int psfr_psd(psfr_ctx* c, int ndraw, const double* draws, int ndir, const double
     if (!c || !draws || !dirs || !poslgs) return set_error(c, PSFR_E_ARG, "NULL argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PSFR_CUDA(c, cudaSetDevice(c->device));
-    int rc = upload_draws(c, ndraw, draws, ndir, dirs, ngs, poslgs, s);
+    int rc = upload_geometry(c, ndraw, draws, ndir, dirs, ngs, poslgs, s);
     if (rc) return rc;
+    if ((rc = upload_draws(c, ndraw, draws, ndir, s))) return rc;
     rc = run_psd(c, ndraw, ndir, ngs, s);
     if (rc) return rc;
     if (out_psd) return from_device(c, out_psd, c->d_psd, (size_t)ndraw * ndir * kN * kN * sizeof(double), s);
@@ -410,13 +415,16 @@ int psfr_compute_batch(psfr_ctx* c, int ndraw, const double* draws, int ndir, co
     if (rc) return rc;
     rc = run_build_kernels(c, 0, nlam, lam.data(), false, true, s);
     if (rc) return rc;
+    rc = upload_geometry(c, ndraw, draws, ndir, dirs, ngs, poslgs, s);
+    if (rc) return rc;
     hot_begin(c);
     c->hot_timed = true;
     const int per_chunk = c->max_planes / ndir;
     const size_t img = (size_t)kPSF * kPSF;
+    bool host_out = false;
     for (int d0 = 0; d0 < ndraw; d0 += per_chunk) {
         const int nd = std::min(per_chunk, ndraw - d0);
-        rc = upload_draws(c, nd, draws + (size_t)d0 * PSFR_DRAW_NPAR, ndir, dirs, ngs, poslgs, s);
+        rc = upload_draws(c, nd, draws + (size_t)d0 * PSFR_DRAW_NPAR, ndir, s);
         if (rc) break;
         if ((rc = run_psd(c, nd, ndir, ngs, s))) break;
         if ((rc = run_structure_function(c, nd * ndir, s))) break;
@@ -429,15 +437,23 @@ int psfr_compute_batch(psfr_ctx* c, int ndraw, const double* draws, int ndir, co
         const bool fit_dev = out_fit && is_device_ptr(out_fit);
         double* fit = fit_dev ? out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR : c->d_fit;
         if (out_fit && (rc = run_fit(c, nd * nlam, kPSF, kPSF, conv, fit, s))) break;
-        if (out_cube && !cube_dev &&
-            (rc = from_device(c, out_cube + (size_t)d0 * nlam * img, conv, (size_t)nd * nlam * img * sizeof(double), s)))
-            break;
-        if (out_fit && !fit_dev &&
-            (rc = from_device(c, out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR, fit,
-                              (size_t)nd * nlam * PSFR_FIT_NPAR * sizeof(double), s)))
-            break;
+        // host outputs: stream-ordered copies (truly asynchronous into pinned memory); one sync below
+        if (out_cube && !cube_dev) {
+            if (cudaMemcpyAsync(out_cube + (size_t)d0 * nlam * img, conv, (size_t)nd * nlam * img * sizeof(double),
+                                cudaMemcpyDefault, s) != cudaSuccess) { rc = set_error(c, PSFR_E_CUDA, "cube copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            host_out = true;
+        }
+        if (out_fit && !fit_dev) {
+            if (cudaMemcpyAsync(out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR, fit,
+                                (size_t)nd * nlam * PSFR_FIT_NPAR * sizeof(double), cudaMemcpyDefault, s) != cudaSuccess) { rc = set_error(c, PSFR_E_CUDA, "fit copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            host_out = true;
+        }
     }
     c->hot_timed = false;
+    if (host_out) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && !rc) rc = set_error(c, PSFR_E_CUDA, "compute_batch: %s", cudaGetErrorString(e));
+    }
     return rc;
 }
 

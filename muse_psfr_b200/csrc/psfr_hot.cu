@@ -114,8 +114,11 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
         const int s = it % kStages, u = it / kStages;
         // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
         int lam = (warp - (int)(((long long)it * p.nlam) % kHotWarps) + kHotWarps) % kHotWarps;
+        // every warp observes every fill, also when it has no wavelength in this item: that keeps
+        // all warps within kStages items of each other, which the per-stage release counter and
+        // the phase parity rely on
+        mbar_wait(full + s, u & 1);
         if (lam < p.nlam) {
-            mbar_wait(full + s, u & 1);
             const double* sD = ring + (size_t)s * 2 * kTile;
             const double* sT = sD + kTile;
             const int item = begin + it;

@@ -127,11 +127,13 @@ struct StoreTransposedPair {
 };
 
 // Re -> row 2m, Im -> row 2m+1 of out[plane][nrows_out][N], column b = (x + N/2) % N,
-// value * scale * (-1)^(row + b)
+// value * scale * (-1)^(row + b).  The sign alternation is the output-side image of an input
+// that was stored centred (fftshift-ed); `alternate` = 0 for an input in natural FFT order.
 struct StoreRealRows {
     double* out;
     int npair, nrows_out, last_valid;
     double scale;
+    int alternate;
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / npair, m = f % npair;
         const int o1 = 2 * m, o2 = o1 + 1;
@@ -141,9 +143,9 @@ struct StoreRealRows {
         for (int i = 0; i < 40; ++i) {
             const int b = lane + 32 * i;
             const double2 z = nat_get(xb, (b + kNH) % kN);
-            const double s1 = ((o1 + b) & 1) ? -scale : scale;
+            const double s1 = (alternate && ((o1 + b) & 1)) ? -scale : scale;
             r1[b] = s1 * z.x;
-            if (ok2) r1[kN + b] = -s1 * z.y;
+            if (ok2) r1[kN + b] = (alternate ? -s1 : s1) * z.y;
         }
     }
 };
@@ -213,7 +215,7 @@ int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
     const double L = 16.0;
     rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
-                     StoreRealRows{c->d_dphi, kPairs, kRows, kNH, 2.0 / (L * L)}, nplanes * kPairs, s);
+                     StoreRealRows{c->d_dphi, kPairs, kRows, kNH, 2.0 / (L * L), 1}, nplanes * kPairs, s);
     if (rc) return rc;
     return launch_finalize_dphi(c, nplanes, s);
 }
@@ -225,7 +227,7 @@ int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s
     // psf/psf.sum(): the sum of the raw PSF is the OTF at the origin = 1/N^2 exactly (T centre);
     // the unnormalised inverse transform carries 1/N^2 as well, so the two cancel.
     return launch_pass(c, LoadHermitianPair{c->d_bt, kNH, kN - 1},
-                       StoreRealRows{out_dev, kNH, kN, kN - 1, 1.0}, kNH, s);
+                       StoreRealRows{out_dev, kNH, kN, kN - 1, 1.0, 1}, kNH, s);
 }
 
 int run_build_otf(Ctx* c, cudaStream_t s) {
@@ -240,7 +242,7 @@ int run_build_otf(Ctx* c, cudaStream_t s) {
     rc = launch_pass(c, LoadEvenRows{c->d_psd}, StoreTransposedPair{c->d_bt, kPairs}, kPairs, s);
     if (rc) return rc;
     rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
-                     StoreRealRows{c->d_otf, kPairs, kRows, kNH, 1.0 / ((double)kN * kN)}, kPairs, s);
+                     StoreRealRows{c->d_otf, kPairs, kRows, kNH, 1.0 / ((double)kN * kN), 0}, kPairs, s);
     if (rc) return rc;
     double centre = 0;
     PSFR_CUDA(c, cudaMemcpyAsync(&centre, c->d_otf + (size_t)kNH * kN + kNH, sizeof(double),
