@@ -158,6 +158,8 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
 /* Introspection used by tests and the bench --------------------------------------- */
 PSFR_API int psfr_get_otf(psfr_ctx* ctx, double* out);            /* [dim/2+2][dim] half-plane telescope OTF */
 PSFR_API int psfr_get_structure_function(psfr_ctx* ctx, int plane, double* out); /* [dim/2+2][dim], transposed half-plane */
+/* test hook: y[i] = the device exp() used for exp(-Dphi/2) (csrc/fast_exp.cuh), x[i] <= 0 */
+PSFR_API int psfr_debug_exp(psfr_ctx* ctx, int n, const double* x, double* y);
 PSFR_API long long psfr_kernel_launches(const psfr_ctx* ctx);     /* kernels launched by this context so far */
 /* device-side duration [ms] of the stage-B row kernel in the last psfr_psf_cube /
  * psfr_compute_batch call (CUDA events on the launching stream), and its launch count */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     'psfr_polyfit': (_I, [_P, _I, _I, _P, _I, _P, _P, _P]),
     'psfr_get_otf': (_I, [_P, _P]),
     'psfr_get_structure_function': (_I, [_P, _I, _P]),
+    'psfr_debug_exp': (_I, [_P, _I, _P, _P]),
     'psfr_kernel_launches': (ctypes.c_longlong, [_P]),
     'psfr_last_hot_timing': (_I, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I), ctypes.POINTER(ctypes.c_longlong)]),
 }
@@ -196,6 +197,12 @@ class Context:
         out = np.empty((self.dim // 2 + 2, self.dim))
         self._check(self._lib.psfr_get_structure_function(self._h, int(plane), ptr(out)))
         return out
+
+    def debug_exp(self, x):
+        x = f64(x)
+        y = np.empty_like(x)
+        self._check(self._lib.psfr_debug_exp(self._h, x.size, ptr(x), ptr(y)))
+        return y
 
     def kernel_launches(self):
         return int(self._lib.psfr_kernel_launches(self._h))

@@ -529,6 +529,17 @@ int psfr_get_structure_function(psfr_ctx* c, int plane, double* out) {
     return from_device(c, out, c->d_dphi + (size_t)plane * kRows * kN, (size_t)kRows * kN * sizeof(double), 0);
 }
 
+int psfr_debug_exp(psfr_ctx* c, int n, const double* x, double* y) {
+    if (!c || !x || !y) return set_error(c, PSFR_E_ARG, "NULL argument");
+    if (n < 1 || (size_t)n > (size_t)c->max_planes * c->max_lambda * kPSF * kPSF)
+        return set_error(c, PSFR_E_CAPACITY, "n=%d exceeds the staging buffer", n);
+    PSFR_CUDA(c, cudaSetDevice(c->device));
+    int rc = to_device(c, c->d_cube, x, (size_t)n * sizeof(double), 0);
+    if (rc) return rc;
+    if ((rc = run_debug_exp(c, c->d_cube, c->d_cube2, n, 0))) return rc;
+    return from_device(c, y, c->d_cube2, (size_t)n * sizeof(double), 0);
+}
+
 long long psfr_kernel_launches(const psfr_ctx* c) { return c ? c->launches : 0; }
 
 int psfr_last_hot_timing(psfr_ctx* c, double* ms, int* launches, long long* psfs) {

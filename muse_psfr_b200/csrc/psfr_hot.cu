@@ -16,6 +16,7 @@
 //    directions of a draw before the transform: the mean over directions, psfrec.py:674,
 //    commutes with the linear transform), keeping the 80 sampled outputs -> 80x80 samples.
 #include "pass_kernel.cuh"
+#include "fast_exp.cuh"
 
 namespace psfr {
 
@@ -110,6 +111,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     __syncthreads();
 
     double* xb = xall + (size_t)warp * G::XBUF;
+#pragma unroll 1
     for (int it = 0; it < count; ++it) {
         const int s = it % kStages, u = it / kStages;
         // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
@@ -123,18 +125,24 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             const double* sT = sD + kTile;
             const int item = begin + it;
             const int plane = item / kPairs, rp = item % kPairs;
+#pragma unroll 1
             for (; lam < p.nlam; lam += kHotWarps) {
-                const double c = __ldg(p.clam + lam);
+                const double negc = -__ldg(p.clam + lam);
                 double2 v[40];
+                // two slots (= four independent exp chains) per basic block
 #pragma unroll
-                for (int i = 0; i < 40; ++i) {
-                    const int n = slot_n(i, lane);
-                    const double t1 = sT[n], t2 = sT[kN + n];
+                for (int i = 0; i < 40; i += 2) {
+                    const int n0 = slot_n(i, lane), n1 = slot_n(i + 1, lane);
+                    const double ta = sT[n0], tb = sT[kN + n0], tc = sT[n1], td = sT[kN + n1];
                     // outside the pupil-autocorrelation support the OTF is exactly zero
-                    if (__all_sync(0xffffffffu, (t1 == 0.0) & (t2 == 0.0))) {
+                    if (__all_sync(0xffffffffu, (ta == 0.0) & (tb == 0.0) & (tc == 0.0) & (td == 0.0))) {
                         v[i] = make_double2(0.0, 0.0);
+                        v[i + 1] = make_double2(0.0, 0.0);
                     } else {
-                        v[i] = make_double2(exp(-c * sD[n]) * t1, exp(-c * sD[kN + n]) * t2);
+                        const double ea = fast_exp(negc * sD[n0]), eb = fast_exp(negc * sD[kN + n0]);
+                        const double ec = fast_exp(negc * sD[n1]), ed = fast_exp(negc * sD[kN + n1]);
+                        v[i] = make_double2(ea * ta, eb * tb);
+                        v[i + 1] = make_double2(ec * tc, ed * td);
                     }
                 }
                 warp_fft<kR3>(v, xb, tw1, tw2, lane);

@@ -100,6 +100,8 @@ int run_structure_function(Ctx* c, int nplanes, cudaStream_t s);
 int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s);
 // context init: pupil + telescope OTF
 int run_build_otf(Ctx* c, cudaStream_t s);
+// test hook: y = fast_exp(x) elementwise
+int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_t s);
 
 // ---- psfr_hot.cu: pruned stage B ----------------------------------------------------
 // row pass with fused exp(-c D) * OTF for nplanes x nlam, then pruned column pass summing

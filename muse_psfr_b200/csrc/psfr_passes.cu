@@ -8,6 +8,7 @@
 // A 2-D transform is two passes; the first writes its output transposed in 32-byte
 // sectors, the second reads contiguous lines again, so no stand-alone transpose exists.
 #include "pass_kernel.cuh"
+#include "fast_exp.cuh"
 
 namespace psfr {
 
@@ -47,8 +48,8 @@ struct LoadOtfRows {
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
             const int n = slot_n(i, lane);
-            v[i] = make_double2(exp(-c * __ldg(d1 + n)) * __ldg(t1 + n),
-                                exp(-c * __ldg(d1 + kN + n)) * __ldg(t1 + kN + n));
+            v[i] = make_double2(fast_exp(-c * __ldg(d1 + n)) * __ldg(t1 + n),
+                                fast_exp(-c * __ldg(d1 + kN + n)) * __ldg(t1 + kN + n));
         }
     }
 };
@@ -228,6 +229,17 @@ int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s
     // the unnormalised inverse transform carries 1/N^2 as well, so the two cancel.
     return launch_pass(c, LoadHermitianPair{c->d_bt, kNH, kN - 1},
                        StoreRealRows{out_dev, kNH, kN, kN - 1, 1.0, 1}, kNH, s);
+}
+
+__global__ void debug_exp_kernel(const double* x, double* y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fast_exp(x[i]);
+}
+
+int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_t s) {
+    debug_exp_kernel<<<(n + 255) / 256, 256, 0, s>>>(x_dev, y_dev, n);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
 }
 
 int run_build_otf(Ctx* c, cudaStream_t s) {

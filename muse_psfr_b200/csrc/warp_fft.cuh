@@ -232,7 +232,8 @@ PSFR_HD void fft_dump(const double2* v, double* sm, int t, int c) {
     for (int u = 0; u < G::NQ; ++u)
 #pragma unroll
         for (int k3 = 0; k3 < R3; ++k3)
-            sm[nat_addr(t + G::TL * u + 64 * k3)] = comp_get(v[u * R3 + k3], c);
+            // nat_addr(t + c) = nat_addr(t) + c + c/16 for c a multiple of 16: constant offsets
+            sm[nat_addr(t) + (G::TL * u + 64 * k3) + ((G::TL * u + 64 * k3) >> 4)] = comp_get(v[u * R3 + k3], c);
 }
 
 // Twiddle tables (host fills them in double precision; see psfr_api.cu / host_check.cu)

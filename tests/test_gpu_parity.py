@@ -309,3 +309,15 @@ def test_kernels_were_launched(psfrec):
     assert ctx.kernel_launches() > 0
     ms, n, psfs = ctx.last_hot_timing()
     assert n == 1 and psfs == 1 and ms > 0
+
+
+def test_device_exp_accuracy(psfrec):
+    """csrc/fast_exp.cuh (the exp of exp(-Dphi/2), psfrec.py:793-794) against numpy/libm."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([-rng.uniform(0, 700, 200000), -10.0 ** rng.uniform(-12, 2.8, 100000),
+                        [0.0, 1e-12, -1e-300, -0.34657359027997264, -0.3465735902799727, -745.0, -1e4]])
+    y = psfrec.get_context().debug_exp(x)
+    ok = x > -690
+    ref = np.exp(x)
+    assert np.abs(y[ok] / ref[ok] - 1).max() < 4.5e-16          # <= 2 ulp
+    assert np.all(y[~ok] < 1e-299) and np.all(y >= 0)            # far below any visible level
