@@ -7,6 +7,7 @@
 //                     analytic Jacobian (fit_psf_cube -> mpdaf moffat_fit, :861-871)
 //   mean / polyfit  : time mean of cubes (:1104) and polynomial smoothing (:1174-1210)
 #include "psfr_internal.h"
+#include "fast_exp.cuh"
 
 namespace psfr {
 
@@ -149,216 +150,209 @@ convolve_kernel(const double* __restrict__ in, const double* __restrict__ ktt,
 }
 
 // ---------------------------------------------------------------- Moffat fit
-// model f = I (1 + ((p-y0)^2 + (q-x0)^2)/a^2)^(-n), parameters x = [I, y0, x0, a, n]
-constexpr int kFitThreads = 128;
+// model f = I (1 + ((p-y0)^2 + (q-x0)^2)/a^2)^(-n), parameters x = [I, y0, x0, a, n].
+// One WARP per image (4 images per CTA): the image sits in shared memory, every lane owns
+// npx/32 pixels, the 21 sums of the normal equations are reduced with xor-shuffles (all lanes
+// end with bit-identical sums, so the 5x5 solve and the LM control flow run redundantly and
+// uniformly in every lane) - no block-level synchronisation at all.
+constexpr int kFitWarps = 4;
 constexpr int kNP = 5;
 constexpr int kNSUM = 21;  // 15 (J^T J upper) + 5 (J^T r) + 1 (cost)
 
-__device__ void block_sum_vec(double* v, int n, double* red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int k = 0; k < n; ++k) {
+// packed-upper index of (i, j), i <= j
+__device__ __forceinline__ constexpr int pk(int i, int j) { return i * kNP - i * (i - 1) / 2 + (j - i); }
+
+__device__ __forceinline__ void warp_sum_vec(double* v) {
+#pragma unroll
+    for (int k = 0; k < kNSUM; ++k) {
         double t = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         v[k] = t;
     }
-    __syncthreads();
-    if (lane == 0)
-        for (int k = 0; k < n; ++k) red[warp * kNSUM + k] = v[k];
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {
-        double t = 0.0;
-        for (int w = 0; w < nw; ++w) t += red[w * kNSUM + k];
-        v[k] = t;
-    }
 }
 
-// accumulate normal equations at x over this thread's pixels
-__device__ void accumulate(const double* __restrict__ img, int ny, int nx, const double* x, double* sums) {
+// accumulate normal equations at x over this lane's pixels, then reduce over the warp
+__device__ __forceinline__ void accumulate(const double* __restrict__ img, int npx, int nx, const double* x,
+                                           double* sums) {
+#pragma unroll
     for (int k = 0; k < kNSUM; ++k) sums[k] = 0.0;
     const double I = x[0], y0 = x[1], x0 = x[2], a = x[3], n = x[4];
-    const double ia2 = 1.0 / (a * a);
-    for (int idx = threadIdx.x; idx < ny * nx; idx += blockDim.x) {
-        const double dp = (double)(idx / nx) - y0, dq = (double)(idx % nx) - x0;
+    const double ia2 = 1.0 / (a * a), ia = 1.0 / a;
+    const int lane = threadIdx.x & 31;
+    int pr = lane / nx, qc = lane % nx;          // once per call; then stepped incrementally
+    const int dpr = 32 / nx, dqc = 32 % nx;
+    for (int idx = lane; idx < npx; idx += 32) {
+        const double dp = (double)pr - y0, dq = (double)qc - x0;
         const double rho2 = (dp * dp + dq * dq) * ia2;
         const double uu = 1.0 + rho2;
         const double lu = log(uu);
-        const double m = exp(-n * lu);             // u^-n
+        const double m = fast_exp(-n * lu);        // u^-n
         const double f = I * m;
         const double g = 2.0 * n * f / uu;          // 2 I n u^(-n-1)
         double J[kNP];
         J[0] = m;
         J[1] = g * dp * ia2;
         J[2] = g * dq * ia2;
-        J[3] = g * rho2 / a;
+        J[3] = g * rho2 * ia;
         J[4] = -f * lu;
         const double r = f - img[idx];
-        int k = 0;
 #pragma unroll
         for (int i = 0; i < kNP; ++i)
 #pragma unroll
-            for (int j = i; j < kNP; ++j) sums[k++] += J[i] * J[j];
+            for (int j = i; j < kNP; ++j) sums[pk(i, j)] = fma(J[i], J[j], sums[pk(i, j)]);
 #pragma unroll
-        for (int i = 0; i < kNP; ++i) sums[15 + i] += J[i] * r;
-        sums[20] += r * r;
+        for (int i = 0; i < kNP; ++i) sums[15 + i] = fma(J[i], r, sums[15 + i]);
+        sums[20] = fma(r, r, sums[20]);
+        pr += dpr;
+        qc += dqc;
+        if (qc >= nx) {
+            qc -= nx;
+            ++pr;
+        }
     }
+    warp_sum_vec(sums);
 }
 
-// solve (A + mu diag(A)) d = -g by Cholesky; A from packed upper sums. returns false if not SPD
-__device__ bool solve_damped(const double* s, double mu, double* d) {
-    double A[kNP][kNP];
-    int k = 0;
-    for (int i = 0; i < kNP; ++i)
-        for (int j = i; j < kNP; ++j) {
-            A[i][j] = A[j][i] = s[k++];
-        }
-    for (int i = 0; i < kNP; ++i) A[i][i] *= (1.0 + mu);
-    double L[kNP][kNP];
-    for (int i = 0; i < kNP; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double t = A[i][j];
-            for (int q = 0; q < j; ++q) t -= L[i][q] * L[j][q];
-            if (i == j) {
-                if (!(t > 0.0)) return false;
-                L[i][i] = sqrt(t);
-            } else {
-                L[i][j] = t / L[j][j];
-            }
-        }
-    double y[kNP];
+// Cholesky of A + mu diag(A) (A from the packed sums), fully unrolled in registers.
+// L holds the factor with the RECIPROCAL of the diagonal on the diagonal.
+__device__ __forceinline__ bool cholesky(const double* s, double mu, double (&L)[kNP][kNP]) {
+    bool ok = true;
+#pragma unroll
     for (int i = 0; i < kNP; ++i) {
-        double t = -s[15 + i];
-        for (int q = 0; q < i; ++q) t -= L[i][q] * y[q];
-        y[i] = t / L[i][i];
-    }
-    for (int i = kNP - 1; i >= 0; --i) {
-        double t = y[i];
-        for (int q = i + 1; q < kNP; ++q) t -= L[q][i] * d[q];
-        d[i] = t / L[i][i];
-    }
-    return true;
-}
-
-// diagonal of A^-1 (A SPD from packed sums), via Cholesky; returns false if singular
-__device__ bool inv_diag(const double* s, double* dg) {
-    double A[kNP][kNP], L[kNP][kNP];
-    int k = 0;
-    for (int i = 0; i < kNP; ++i)
-        for (int j = i; j < kNP; ++j) A[i][j] = A[j][i] = s[k++];
-    for (int i = 0; i < kNP; ++i)
+#pragma unroll
         for (int j = 0; j <= i; ++j) {
-            double t = A[i][j];
-            for (int q = 0; q < j; ++q) t -= L[i][q] * L[j][q];
+            double t = s[pk(j, i)];
+            if (i == j) t *= (1.0 + mu);
+#pragma unroll
+            for (int q = 0; q < j; ++q) t = fma(-L[i][q], L[j][q], t);
             if (i == j) {
-                if (!(t > 0.0)) return false;
-                L[i][i] = sqrt(t);
+                ok = ok && (t > 0.0);
+                L[i][i] = rsqrt(t);
             } else {
-                L[i][j] = t / L[j][j];
+                L[i][j] = t * L[j][j];
             }
         }
-    for (int c = 0; c < kNP; ++c) {
-        double y[kNP], z[kNP];
-        for (int i = 0; i < kNP; ++i) {
-            double t = (i == c) ? 1.0 : 0.0;
-            for (int q = 0; q < i; ++q) t -= L[i][q] * y[q];
-            y[i] = t / L[i][i];
-        }
-        for (int i = kNP - 1; i >= 0; --i) {
-            double t = y[i];
-            for (int q = i + 1; q < kNP; ++q) t -= L[q][i] * z[q];
-            z[i] = t / L[i][i];
-        }
-        dg[c] = z[c];
     }
-    return true;
+    return ok;
 }
 
-__global__ void __launch_bounds__(kFitThreads)
-fit_kernel(const double* __restrict__ imgs, int ny, int nx, double* __restrict__ out) {
+// solve L L^T z = b in place
+__device__ __forceinline__ void chol_solve(const double (&L)[kNP][kNP], double* z) {
+#pragma unroll
+    for (int i = 0; i < kNP; ++i) {
+        double t = z[i];
+#pragma unroll
+        for (int q = 0; q < i; ++q) t = fma(-L[i][q], z[q], t);
+        z[i] = t * L[i][i];
+    }
+#pragma unroll
+    for (int i = kNP - 1; i >= 0; --i) {
+        double t = z[i];
+#pragma unroll
+        for (int q = i + 1; q < kNP; ++q) t = fma(-L[q][i], z[q], t);
+        z[i] = t * L[i][i];
+    }
+}
+
+__global__ void __launch_bounds__(kFitWarps * 32)
+fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __restrict__ out) {
     extern __shared__ double sm[];
-    double* img = sm;                       // ny*nx
-    double* red = sm + ny * nx;             // 4 * kNSUM
-    double* colw = red + 4 * kNSUM;         // nx
-    __shared__ double xs[kNP];
-    __shared__ int ipk[2];
-    const int npx = ny * nx, tid = threadIdx.x;
-    const double* src = imgs + (size_t)blockIdx.x * npx;
-    for (int i = tid; i < npx; i += blockDim.x) img[i] = src[i];
-    __syncthreads();
+    const int npx = ny * nx, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int image = blockIdx.x * kFitWarps + warp;
+    if (image >= nimg) return;                       // whole warp leaves; no block barrier is used below
+    double* img = sm + (size_t)warp * (npx + nx);    // npx pixels + nx column weights
+    double* colw = img + npx;
+    const double* src = imgs + (size_t)image * npx;
+    for (int i = lane; i < npx; i += 32) img[i] = src[i];
+    __syncwarp();
     // ---- start point as mpdaf: peak pixel, width from Image.moments(), n = 2
-    for (int q = tid; q < nx; q += blockDim.x) {
+    for (int q = lane; q < nx; q += 32) {
         double t = 0.0;
         for (int p = 0; p < ny; ++p) t += p * fabs(img[p * nx + q]);
         colw[q] = t;
     }
-    __syncthreads();
-    if (tid == 0) {
-        int qb = 0;
-        for (int q = 1; q < nx; ++q)
-            if (colw[q] > colw[qb]) qb = q;
-        double num = 0.0, den = 0.0;
-        for (int p = 0; p < ny; ++p) {
-            const double v = img[p * nx + qb];
-            num += fabs((p - qb) * v);
-            den += fabs(v);
-        }
-        const double wp = sqrt(num / den);
-        int best = 0;
-        for (int i = 1; i < npx; ++i)
-            if (img[i] > img[best]) best = i;
-        ipk[0] = best / nx;
-        ipk[1] = best % nx;
-        const double fwhm0 = wp * 2.0 * sqrt(2.0 * log(2.0));
-        xs[0] = img[best];
-        xs[1] = ipk[0];
-        xs[2] = ipk[1];
-        xs[3] = fwhm0 / (2.0 * sqrt(sqrt(2.0) - 1.0));
-        xs[4] = 2.0;
+    __syncwarp();
+    // first maximum of colw (column of the weighted sums) and of the image (peak pixel)
+    double bestw = -1.0, bestv = -1e300;
+    int qb = 0, ib = 0;
+    for (int q = lane; q < nx; q += 32)
+        if (colw[q] > bestw) { bestw = colw[q]; qb = q; }
+    for (int i = lane; i < npx; i += 32)
+        if (img[i] > bestv) { bestv = img[i]; ib = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ow = __shfl_xor_sync(0xffffffffu, bestw, o);
+        const int oq = __shfl_xor_sync(0xffffffffu, qb, o);
+        if (ow > bestw || (ow == bestw && oq < qb)) { bestw = ow; qb = oq; }
+        const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ib, o);
+        if (ov > bestv || (ov == bestv && oi < ib)) { bestv = ov; ib = oi; }
     }
-    __syncthreads();
+    double num = 0.0, den = 0.0;
+    for (int p = lane; p < ny; p += 32) {
+        const double v = img[p * nx + qb];
+        num += fabs((p - qb) * v);
+        den += fabs(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, o);
+        den += __shfl_xor_sync(0xffffffffu, den, o);
+    }
     double x[kNP], sums[kNSUM], trial[kNSUM], xt[kNP], d[kNP];
-    for (int i = 0; i < kNP; ++i) x[i] = xs[i];
-    accumulate(img, ny, nx, x, sums);
-    block_sum_vec(sums, kNSUM, red);
+    {
+        const double wp = sqrt(num / den);
+        const double fwhm0 = wp * 2.0 * sqrt(2.0 * log(2.0));
+        x[0] = bestv;
+        x[1] = ib / nx;
+        x[2] = ib % nx;
+        x[3] = fwhm0 / (2.0 * sqrt(sqrt(2.0) - 1.0));
+        x[4] = 2.0;
+    }
+    accumulate(img, npx, nx, x, sums);
     double mu = 1e-3, nu = 2.0;
     int iter = 0, status = -1;
     const int max_iter = 200;
+    constexpr int dia[kNP] = {pk(0, 0), pk(1, 1), pk(2, 2), pk(3, 3), pk(4, 4)};
+    double L[kNP][kNP];
     for (iter = 1; iter <= max_iter; ++iter) {
-        // every thread runs the identical 5x5 solve on identical data
-        bool ok = solve_damped(sums, mu, d);
-        if (!ok) {
+        // every lane runs the identical solve on bit-identical sums
+        if (!cholesky(sums, mu, L)) {
             mu *= nu;
             nu *= 2.0;
-            if (mu > 1e12) break;
+            if (mu > 1e15) break;
             continue;
         }
+#pragma unroll
+        for (int i = 0; i < kNP; ++i) d[i] = -sums[15 + i];
+        chol_solve(L, d);
         double dn = 0.0, xn = 0.0, pred = 0.0;
+#pragma unroll
         for (int i = 0; i < kNP; ++i) {
             xt[i] = x[i] + d[i];
-            const double sc = sqrt(sums[i == 0 ? 0 : i == 1 ? 5 : i == 2 ? 9 : i == 3 ? 12 : 14]);  // |J col|
-            dn += (d[i] * sc) * (d[i] * sc);
-            xn += (x[i] * sc) * (x[i] * sc);
-        }
-        // predicted decrease of the cost r.r : -d.(2 g) - d.A.d = d.(mu D d - g)
-        {
-            const int dia[kNP] = {0, 5, 9, 12, 14};
-            for (int i = 0; i < kNP; ++i) pred += d[i] * (mu * sums[dia[i]] * d[i] - sums[15 + i]);
+            const double sc2 = sums[dia[i]];                  // |J column|^2
+            dn = fma(d[i] * d[i], sc2, dn);
+            xn = fma(x[i] * x[i], sc2, xn);
+            // predicted decrease of r.r : d.(mu D d - g)
+            pred += d[i] * (mu * sc2 * d[i] - sums[15 + i]);
         }
         if (!(xt[3] > 0.0) || !(xt[4] > 0.0) || !isfinite(xt[0])) {
             mu *= nu;
             nu *= 2.0;
-            if (mu > 1e12) break;
+            if (mu > 1e15) break;
             continue;
         }
-        accumulate(img, ny, nx, xt, trial);
-        block_sum_vec(trial, kNSUM, red);
+        accumulate(img, npx, nx, xt, trial);
         const double actual = sums[20] - trial[20];
         // near the minimum the cost is flat to rounding: tolerate a noise-level increase so that
         // Gauss-Newton steps keep contracting, and stop on the (column-scaled) step size
         const bool small = dn <= 1e-22 * (xn + 1e-300);            // relative step <= 1e-11
         if (isfinite(trial[20]) && actual >= -1e-13 * sums[20]) {
             const double rho = pred > 0.0 ? actual / pred : 1.0;
+#pragma unroll
             for (int i = 0; i < kNP; ++i) x[i] = xt[i];
+#pragma unroll
             for (int k = 0; k < kNSUM; ++k) sums[k] = trial[k];
             const double t = 2.0 * rho - 1.0;
             mu *= fmax(1.0 / 3.0, 1.0 - t * t * t);
@@ -378,8 +372,8 @@ fit_kernel(const double* __restrict__ imgs, int ny, int nx, double* __restrict__
             if (mu > 1e15) break;
         }
     }
-    if (tid == 0) {
-        double* o = out + (size_t)blockIdx.x * PSFR_FIT_NPAR;
+    if (lane == 0) {
+        double* o = out + (size_t)image * PSFR_FIT_NPAR;
         const double a = fabs(x[3]), n = x[4];
         const double kf = 2.0 * sqrt(pow(2.0, 1.0 / n) - 1.0);
         o[PSFR_FIT_PEAK] = x[0];
@@ -390,11 +384,17 @@ fit_kernel(const double* __restrict__ imgs, int ny, int nx, double* __restrict__
         o[PSFR_FIT_FWHM] = a * kf;
         o[PSFR_FIT_CHISQ] = sums[20];
         o[PSFR_FIT_ITER] = (status > 0) ? (double)status : -(double)(iter > max_iter ? max_iter : iter);
-        double dg[kNP];
         const double dof = (double)(npx - kNP);
-        if (inv_diag(sums, dg)) {
+        if (cholesky(sums, 0.0, L)) {
             double e[kNP];
-            for (int i = 0; i < kNP; ++i) e[i] = sqrt(fabs(dg[i]) * fabs(sums[20] / dof));
+#pragma unroll
+            for (int c = 0; c < kNP; ++c) {
+                double z[kNP];
+#pragma unroll
+                for (int i = 0; i < kNP; ++i) z[i] = (i == c) ? 1.0 : 0.0;
+                chol_solve(L, z);
+                e[c] = sqrt(fabs(z[c]) * fabs(sums[20] / dof));
+            }
             o[PSFR_FIT_ERR_PEAK] = e[0];
             o[PSFR_FIT_ERR_Y0] = e[1];
             o[PSFR_FIT_ERR_X0] = e[2];
@@ -536,16 +536,14 @@ int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_
 }
 
 int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s) {
-    const size_t smem = (size_t)(ny * nx + 4 * kNSUM + nx) * sizeof(double);
-    if (smem > 48 * 1024) {
-        static bool attr = false;
-        if (!attr) {
-            PSFR_CUDA(c, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr = true;
-        }
-        if (smem > 200 * 1024) return set_error(c, PSFR_E_UNSUPPORTED, "image %dx%d too large for the fitter", ny, nx);
+    const size_t smem = (size_t)kFitWarps * (ny * nx + nx) * sizeof(double);
+    if (smem > 200 * 1024) return set_error(c, PSFR_E_UNSUPPORTED, "image %dx%d too large for the fitter", ny, nx);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        PSFR_CUDA(c, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
     }
-    fit_kernel<<<nimg, kFitThreads, smem, s>>>(img_dev, ny, nx, fit_dev);
+    fit_kernel<<<(nimg + kFitWarps - 1) / kFitWarps, kFitWarps * 32, smem, s>>>(img_dev, nimg, ny, nx, fit_dev);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }
