@@ -155,6 +155,15 @@ PSFR_API int psfr_mean_refit(psfr_ctx* ctx, int ncube, int nlam, const double* c
 PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* lambda_nm, int deg,
                  const double* y, double* coef, void* stream);
 
+/* Options.  PSFR_OPT_EXP_CUT (default 64): in the pruned stage-B row pass (psfr_psf_cube,
+ * psfr_compute_batch) entries of exp(-Dphi/2) smaller than exp(-cut) are flushed to zero and
+ * row pairs that are below the cut everywhere are not transformed.  The OTF peak is 1, so
+ * the default drops terms below 1.6e-28 of it - twelve orders of magnitude under the FP64
+ * rounding of the transform itself.  A value >= 745 (exp underflows) disables the cut.
+ * psfr_psd_to_psf (full-grid parity mode) never applies it. */
+enum { PSFR_OPT_EXP_CUT = 1 };
+PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
+
 /* Introspection used by tests and the bench --------------------------------------- */
 PSFR_API int psfr_get_otf(psfr_ctx* ctx, double* out);            /* [dim/2+2][dim] half-plane telescope OTF */
 PSFR_API int psfr_get_structure_function(psfr_ctx* ctx, int plane, double* out); /* [dim/2+2][dim], transposed half-plane */

@@ -22,6 +22,7 @@ AO_DIM = 80
 PSF_DIM = 40
 
 E_CUDA, E_ARG, E_UNSUPPORTED, E_CAPACITY, E_STATE = -1, -2, -3, -4, -5
+OPT_EXP_CUT = 1
 
 
 class PsfrError(RuntimeError):
@@ -53,6 +54,7 @@ _SIGNATURES = {
     'psfr_compute_batch': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
     'psfr_mean_refit': (_I, [_P, _I, _I, _P, _P, _P, _P]),
     'psfr_polyfit': (_I, [_P, _I, _I, _P, _I, _P, _P, _P]),
+    'psfr_set_option': (_I, [_P, _I, _D]),
     'psfr_get_otf': (_I, [_P, _P]),
     'psfr_get_structure_function': (_I, [_P, _I, _P]),
     'psfr_debug_exp': (_I, [_P, _I, _P, _P]),
@@ -187,6 +189,9 @@ class Context:
         coef = np.empty((y.shape[0], deg + 1))
         self._check(self._lib.psfr_polyfit(self._h, y.shape[0], lam.size, ptr(lam), int(deg), ptr(y), ptr(coef), stream))
         return coef
+
+    def set_option(self, key, value):
+        self._check(self._lib.psfr_set_option(self._h, int(key), float(value)))
 
     def get_otf(self):
         out = np.empty((self.dim // 2 + 2, self.dim))

@@ -154,7 +154,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_bt); cudaFree(c->d_dphi); cudaFree(c->d_ybuf); cudaFree(c->d_samp); cudaFree(c->d_ao);
     cudaFree(c->d_draws); cudaFree(c->d_misc); cudaFree(c->d_lam); cudaFree(c->d_kidx); cudaFree(c->d_frac);
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
-    cudaFree(c->d_fit); cudaFree(c->d_poly);
+    cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     HotTimer* t = timer_of(c);
     if (t) {
@@ -214,6 +214,8 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_psd, P * kN * kN));
     CK(dev_alloc(c, &c->d_bt, P * kN * kRows));
     CK(dev_alloc(c, &c->d_dphi, P * kRows * kN));
+    CK(dev_alloc(c, &c->d_dmin, P * kRows));
+    CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNS * kRows));
     CK(dev_alloc(c, &c->d_samp, P * LM * kNS * kNS));
     CK(dev_alloc(c, &c->d_ao, P * kAO * kAO));
@@ -538,6 +540,18 @@ int psfr_debug_exp(psfr_ctx* c, int n, const double* x, double* y) {
     if (rc) return rc;
     if ((rc = run_debug_exp(c, c->d_cube, c->d_cube2, n, 0))) return rc;
     return from_device(c, y, c->d_cube2, (size_t)n * sizeof(double), 0);
+}
+
+int psfr_set_option(psfr_ctx* c, int key, double value) {
+    if (!c) return set_error(c, PSFR_E_ARG, "NULL context");
+    switch (key) {
+        case PSFR_OPT_EXP_CUT:
+            if (!(value > 0)) return set_error(c, PSFR_E_ARG, "exp cut must be positive (got %g)", value);
+            c->exp_cut = value;
+            return PSFR_OK;
+        default:
+            return set_error(c, PSFR_E_ARG, "unknown option %d", key);
+    }
 }
 
 long long psfr_kernel_launches(const psfr_ctx* c) { return c ? c->launches : 0; }

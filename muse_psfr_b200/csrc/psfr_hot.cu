@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -67,6 +70,9 @@ struct HotParams {
     double2* Y;            // [nplanes][nlam][kNS][kRows]
     const double* clam;    // [nlam]
     const uint16_t* kidx;  // [nlam][kNS]
+    const double* dmin;    // [nplanes][kRows] smallest D of each row (finalize_dphi_kernel)
+    int* next_item;        // work counter, zeroed before the launch
+    double cut;            // OTF entries with c*D > cut (exp < e^-cut) are flushed to zero
     int nplanes, nlam;
 };
 
@@ -75,27 +81,32 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);   // per-stage count of warps done with it
+    volatile int* item_of = released + kStages;               // per-stage work item (-1: no more work)
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
     double* ring = reinterpret_cast<double*>(tw2 + G::TW2);   // [stage][D tile | T tile]
     double* xall = ring + (size_t)kStages * 2 * kTile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // static partition of the (plane, row pair) items over the persistent CTAs
     const int items = p.nplanes * kPairs;
-    const int per = items / gridDim.x, rem = items % gridDim.x;
-    const int begin = blockIdx.x * per + min((int)blockIdx.x, rem);
-    const int count = per + ((int)blockIdx.x < rem ? 1 : 0);
 
-    // TMA bulk loads of item `it` (two rows of D and of the telescope OTF) into its ring stage
-    auto issue = [&](int it) {
-        const int s = it % kStages;
-        const int item = begin + it;
-        const int plane = item / kPairs, rp = item % kPairs;
-        double* dst = ring + (size_t)s * 2 * kTile;
-        mbar_expect_tx(full + s, 2 * kTileBytes);
-        tma_load_1d(dst, p.D + ((size_t)plane * kRows + 2 * rp) * kN, kTileBytes, full + s);
-        tma_load_1d(dst + kTile, p.T + (size_t)(2 * rp) * kN, kTileBytes, full + s);
+    // Work items (plane, row pair) are handed out by a global counter: with the underflow cut
+    // the cost of an item ranges from "write zeros" to nlam full transforms, so a static
+    // partition would leave most CTAs idle.  The fetching thread stages the two rows of D and
+    // of the telescope OTF with TMA bulk loads; the item id travels through shared memory and
+    // is published by the mbarrier phase (arrive has release, try_wait acquire semantics).
+    auto issue = [&](int s) {
+        const int item = atomicAdd(p.next_item, 1);
+        if (item < items) {
+            const int plane = item / kPairs, rp = item % kPairs;
+            double* dst = ring + (size_t)s * 2 * kTile;
+            item_of[s] = item;
+            mbar_expect_tx(full + s, 2 * kTileBytes);
+            tma_load_1d(dst, p.D + ((size_t)plane * kRows + 2 * rp) * kN, kTileBytes, full + s);
+            tma_load_1d(dst + kTile, p.T + (size_t)(2 * rp) * kN, kTileBytes, full + s);
+        } else {
+            item_of[s] = -1;
+            mbar_arrive(full + s);
+        }
     };
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
@@ -106,41 +117,65 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int it = 0; it < kStages && it < count; ++it) issue(it);
+        for (int s = 0; s < kStages; ++s) issue(s);
     }
     __syncthreads();
 
     double* xb = xall + (size_t)warp * G::XBUF;
 #pragma unroll 1
-    for (int it = 0; it < count; ++it) {
+    for (int it = 0;; ++it) {
         const int s = it % kStages, u = it / kStages;
-        // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
-        int lam = (warp - (int)(((long long)it * p.nlam) % kHotWarps) + kHotWarps) % kHotWarps;
         // every warp observes every fill, also when it has no wavelength in this item: that keeps
         // all warps within kStages items of each other, which the per-stage release counter and
-        // the phase parity rely on
+        // the phase parity rely on.  Fills are issued in iteration order, so the first -1 a warp
+        // sees is followed by -1 only and no TMA is in flight when the CTA retires.
         mbar_wait(full + s, u & 1);
+        const int item = item_of[s];
+        if (item < 0) break;
+        // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
+        int lam = (warp - (int)(((long long)it * p.nlam) % kHotWarps) + kHotWarps) % kHotWarps;
         if (lam < p.nlam) {
             const double* sD = ring + (size_t)s * 2 * kTile;
             const double* sT = sD + kTile;
-            const int item = begin + it;
             const int plane = item / kPairs, rp = item % kPairs;
+            const double dm = fmin(__ldg(p.dmin + (size_t)plane * kRows + 2 * rp),
+                                   __ldg(p.dmin + (size_t)plane * kRows + 2 * rp + 1));
 #pragma unroll 1
             for (; lam < p.nlam; lam += kHotWarps) {
-                const double negc = -__ldg(p.clam + lam);
+                const double cl = __ldg(p.clam + lam);
+                double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
+                if (cl * dm > p.cut) {
+                    // both rows are below the cut everywhere: their transform is zero
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int y = lane + 32 * i;
+                        if (y < kNS) {
+                            double2* o = out + (size_t)y * kRows;
+                            o[0] = make_double2(0.0, 0.0);
+                            o[1] = make_double2(0.0, 0.0);
+                        }
+                    }
+                    continue;
+                }
+                const double negc = -cl, ncut = -p.cut;
                 double2 v[40];
                 // two slots (= four independent exp chains) per basic block
 #pragma unroll
                 for (int i = 0; i < 40; i += 2) {
                     const int n0 = slot_n(i, lane), n1 = slot_n(i + 1, lane);
                     const double ta = sT[n0], tb = sT[kN + n0], tc = sT[n1], td = sT[kN + n1];
-                    // outside the pupil-autocorrelation support the OTF is exactly zero
-                    if (__all_sync(0xffffffffu, (ta == 0.0) & (tb == 0.0) & (tc == 0.0) & (td == 0.0))) {
+                    const double xa = negc * sD[n0], xb_ = negc * sD[kN + n0];
+                    const double xc = negc * sD[n1], xd = negc * sD[kN + n1];
+                    // outside the pupil-autocorrelation support the OTF is exactly zero; below the
+                    // underflow cut it is flushed to zero
+                    const bool dead = ((ta == 0.0) | (xa < ncut)) & ((tb == 0.0) | (xb_ < ncut)) &
+                                      ((tc == 0.0) | (xc < ncut)) & ((td == 0.0) | (xd < ncut));
+                    if (__all_sync(0xffffffffu, dead)) {
                         v[i] = make_double2(0.0, 0.0);
                         v[i + 1] = make_double2(0.0, 0.0);
                     } else {
-                        const double ea = fast_exp(negc * sD[n0]), eb = fast_exp(negc * sD[kN + n0]);
-                        const double ec = fast_exp(negc * sD[n1]), ed = fast_exp(negc * sD[kN + n1]);
+                        const double ea = fast_exp(xa), eb = fast_exp(xb_);
+                        const double ec = fast_exp(xc), ed = fast_exp(xd);
                         v[i] = make_double2(ea * ta, eb * tb);
                         v[i + 1] = make_double2(ec * tc, ed * td);
                     }
@@ -163,7 +198,6 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     }
                     __syncwarp();
                 }
-                double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int y = lane + 32 * i;
@@ -175,18 +209,16 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 }
             }
         }
-        // release the stage; the last warp to do so refills it with item it + kStages
+        // release the stage; the last warp to do so refills it with the next work item
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
             const int old = atomicAdd(released + s, 1);
             if (old == kHotWarps - 1) {
                 atomicExch(released + s, 0);
-                if (it + kStages < count) {
-                    __threadfence_block();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(it + kStages);
-                }
+                __threadfence_block();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(s);
             }
         }
     }
@@ -256,9 +288,11 @@ int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
         attr_set = true;
     }
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, nplanes, nlam};
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_dmin, c->d_counter,
+                c->exp_cut, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * kPairs) grid = nplanes * kPairs;
+    PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
     int rc = hot_event(c, 0, s);
     if (rc) return rc;
     hot_rows_kernel<<<grid, kHotWarps * 32, kHotSmem, s>>>(p, c->d_tw);

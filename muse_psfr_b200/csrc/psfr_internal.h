@@ -48,6 +48,9 @@ struct Ctx {
     double* d_psd = nullptr;     // [max_planes][N][N]
     double2* d_bt = nullptr;     // [max_planes][N][kRows] transposed row-pass output (full mode)
     double* d_dphi = nullptr;    // [max_planes][kRows][N] structure function (transposed half-plane)
+    double* d_dmin = nullptr;    // [max_planes][kRows] smallest structure-function value of each row
+    int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel
+    double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][kRows] pruned row-pass output
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples
     double* d_ao = nullptr;      // [max_planes][80][80] AO-zone PSD (centred, reference orientation)

@@ -189,21 +189,35 @@ __global__ void stash_centre_kernel(const double* d, double* centre, int nplanes
     if (p < nplanes) centre[p] = d[(size_t)p * kRows * kN + (size_t)kNH * kN + kNH];
 }
 
-// D[a][b] = Draw[N/2][N/2] - Draw[a][b], pad row zero (psfrec.py:721: 2*(bg[0,0] - bg))
-__global__ void finalize_dphi2_kernel(double* d, const double* centre, int nplanes) {
-    const size_t per = (size_t)kRows * kN;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= per * nplanes) return;
-    const size_t plane = idx / per, r = idx % per;
-    d[idx] = (r >= (size_t)(kNH + 1) * kN) ? 0.0 : centre[plane] - d[idx];
+// D[a][b] = Draw[N/2][N/2] - Draw[a][b], pad row zero (psfrec.py:721: 2*(bg[0,0] - bg)); one
+// block per row, which also records the smallest D of the row for the underflow cut of stage B
+__global__ void __launch_bounds__(256)
+finalize_dphi_kernel(double* d, const double* centre, double* dmin) {
+    __shared__ double red[8];
+    const int row = blockIdx.x % kRows, plane = blockIdx.x / kRows;
+    double* r = d + ((size_t)plane * kRows + row) * kN;
+    const double c0 = centre[plane];
+    double m = 1e300;
+    for (int b = threadIdx.x; b < kN; b += blockDim.x) {
+        const double v = (row > kNH) ? 0.0 : c0 - r[b];
+        r[b] = v;
+        m = fmin(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmin(m, red[w]);
+        dmin[(size_t)plane * kRows + row] = m;
+    }
 }
 
 static int launch_finalize_dphi(Ctx* c, int nplanes, cudaStream_t s) {
     double* centre = c->d_misc + kMiscCentre;  // scratch area reserved for plane centres
     stash_centre_kernel<<<(nplanes + 127) / 128, 128, 0, s>>>(c->d_dphi, centre, nplanes);
     PSFR_LAUNCH_CHECK(c);
-    const size_t total = (size_t)nplanes * kRows * kN;
-    finalize_dphi2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->d_dphi, centre, nplanes);
+    finalize_dphi_kernel<<<nplanes * kRows, 256, 0, s>>>(c->d_dphi, centre, c->d_dmin);
     PSFR_LAUNCH_CHECK(c);
     c->planes_struct = nplanes;
     return PSFR_OK;
