@@ -1,4 +1,9 @@
 // Shared pass-kernel template: one warp per length-N line, loader/storer functors.
+//
+// N = NF * 1280.  The warp runs NF interleaved 1280-point transforms (sub-sequence s holds
+// x[NF m + s]) and dumps each in natural order; for NF = 2 one combine step
+//   X[k] = F0[k] + w_N^k F1[k],   X[k + 1280] = F0[k] - w_N^k F1[k]
+// turns the two dumps into the two halves of the length-2560 spectrum in place.
 #pragma once
 #include "psfr_internal.h"
 #include "warp_fft.cuh"
@@ -7,52 +12,81 @@ namespace psfr {
 
 using G = FftGeom<kR3>;
 constexpr int kPassWarps = 4;
-constexpr size_t kPassSmem = (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
-                             (size_t)kPassWarps * 2 * G::XBUF * sizeof(double);
-
-// index of register slot i in the load layout
-__device__ __forceinline__ int slot_n(int i, int lane) { return (i & 7) * (kN / 8) + lane + 32 * (i >> 3); }
-
-// all storers start from the natural-order dump: re in xb[0..), im in xb[XBUF..)
-__device__ __forceinline__ double2 nat_get(const double* xb, int k) {
-    return make_double2(xb[nat_addr(k)], xb[G::XBUF + nat_addr(k)]);
+template <int NF>
+constexpr size_t pass_smem() {
+    return (size_t)(G::TW1 + G::TW2) * sizeof(double2) + (size_t)kPassWarps * NF * 2 * G::XBUF * sizeof(double);
 }
 
+// index of register slot i in the load layout of the 1280-point warp transform
+__device__ __forceinline__ int slot_n(int i, int lane) { return (i & 7) * (kNB / 8) + lane + 32 * (i >> 3); }
+// element of the length-N line that slot i of sub-sequence `sub` holds
+template <int NF>
+__device__ __forceinline__ int slot_e(int i, int lane, int sub) { return NF * slot_n(i, lane) + sub; }
 
-template <class Loader, class Storer>
+// all storers start from the natural-order dumps: output k of the length-N spectrum sits in
+// block k / 1280 (re in [0, XBUF), im in [XBUF, 2 XBUF) of that block)
+template <int NF>
+__device__ __forceinline__ double2 nat_get(const double* xb, int k) {
+    const int q = (NF == 1) ? 0 : k / kNB, kk = (NF == 1) ? k : k % kNB;
+    const double* b = xb + (size_t)q * 2 * G::XBUF;
+    return make_double2(b[nat_addr(kk)], b[G::XBUF + nat_addr(kk)]);
+}
+
+template <int NF, class Loader, class Storer>
 __global__ void __launch_bounds__(kPassWarps * 32)
-pass_kernel(Loader ld, Storer st, int nfft, const double2* __restrict__ g_tw) {
+pass_kernel(Loader ld, Storer st, int nfft, const double2* __restrict__ g_tw, const double2* __restrict__ g_twc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* tw1 = reinterpret_cast<double2*>(smem_raw);
     double2* tw2 = tw1 + G::TW1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* xb = reinterpret_cast<double*>(tw2 + G::TW2) + (size_t)warp * 2 * G::XBUF;
+    double* xb = reinterpret_cast<double*>(tw2 + G::TW2) + (size_t)warp * NF * 2 * G::XBUF;
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
     __syncthreads();
     for (int f = blockIdx.x * kPassWarps + warp; f < nfft; f += gridDim.x * kPassWarps) {
-        double2 v[40];
-        ld(f, lane, v);
-        warp_fft<kR3>(v, xb, tw1, tw2, lane);
-        fft_dump<kR3>(v, xb, lane, 0);
-        fft_dump<kR3>(v, xb + G::XBUF, lane, 1);
-        __syncwarp();
+#pragma unroll 1
+        for (int sub = 0; sub < NF; ++sub) {
+            double2 v[40];
+            ld(f, lane, v, sub);
+            // exchange scratch = the last dump region, which no earlier sub-sequence has filled
+            warp_fft<kR3>(v, xb + (size_t)(2 * NF - 1) * G::XBUF, tw1, tw2, lane);
+            __syncwarp();
+            fft_dump<kR3>(v, xb + (size_t)sub * 2 * G::XBUF, lane, 0);
+            fft_dump<kR3>(v, xb + (size_t)sub * 2 * G::XBUF + G::XBUF, lane, 1);
+            __syncwarp();
+        }
+        if (NF == 2) {
+            double* b0 = xb;
+            double* b1 = xb + 2 * G::XBUF;
+#pragma unroll 4
+            for (int i = 0; i < 40; ++i) {
+                const int k = lane + 32 * i, a = nat_addr(k);
+                const double2 w = __ldg(g_twc + k);
+                const double2 f0 = make_double2(b0[a], b0[G::XBUF + a]);
+                const double2 f1 = cmul(make_double2(b1[a], b1[G::XBUF + a]), w);
+                b0[a] = f0.x + f1.x;
+                b0[G::XBUF + a] = f0.y + f1.y;
+                b1[a] = f0.x - f1.x;
+                b1[G::XBUF + a] = f0.y - f1.y;
+            }
+            __syncwarp();
+        }
         st(f, lane, xb);
         __syncwarp();
     }
 }
 
-template <class Loader, class Storer>
+template <int NF, class Loader, class Storer>
 static int launch_pass(Ctx* c, Loader ld, Storer st, int nfft, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(pass_kernel<Loader, Storer>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassSmem));
+        PSFR_CUDA(c, cudaFuncSetAttribute(pass_kernel<NF, Loader, Storer>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem<NF>()));
         attr_set = true;
     }
     int grid = (nfft + kPassWarps - 1) / kPassWarps;
     const int cap = c->sm_count * 8;
     if (grid > cap) grid = cap;
-    pass_kernel<Loader, Storer><<<grid, kPassWarps * 32, kPassSmem, s>>>(ld, st, nfft, c->d_tw);
+    pass_kernel<NF, Loader, Storer><<<grid, kPassWarps * 32, pass_smem<NF>(), s>>>(ld, st, nfft, c->d_tw, c->d_twc);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }

@@ -53,8 +53,10 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
 static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStream_t s) {
     if (nlam < 1 || nlam > c->max_lambda)
         return set_error(c, PSFR_E_CAPACITY, "nlam=%d outside [1, %d]", nlam, c->max_lambda);
+    const int kN = c->N;
     std::vector<double> cl(nlam), fr((size_t)nlam * kPSF);
     std::vector<uint16_t> kx((size_t)nlam * kNS);
+    std::vector<double2> ws(c->NF == 2 ? (size_t)nlam * 2 * kNS : 0);
     for (int l = 0; l < nlam; ++l) {
         const double lb = lam_host[l];
         if (!(lb > 0)) return set_error(c, PSFR_E_ARG, "wavelength %g nm is not positive", lb);
@@ -73,7 +75,15 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
             kx[(size_t)l * kNS + 2 * y] = (uint16_t)((origin + r0 + kN / 2) % kN);
             kx[(size_t)l * kNS + 2 * y + 1] = (uint16_t)((origin + r0 + 1 + kN / 2) % kN);
         }
+        if (c->NF == 2)
+            for (int j = 0; j < kNS; ++j) {
+                const long k = kx[(size_t)l * kNS + j];
+                ws[((size_t)l * 2) * kNS + j] = unit_root(k, kN);
+                ws[((size_t)l * 2 + 1) * kNS + j] = unit_root((kN - k) % kN, kN);
+            }
     }
+    if (c->NF == 2)
+        PSFR_CUDA(c, cudaMemcpyAsync(c->d_wsamp, ws.data(), ws.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_lam, cl.data(), nlam * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_frac, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kidx, kx.data(), kx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
@@ -155,6 +165,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_draws); cudaFree(c->d_misc); cudaFree(c->d_lam); cudaFree(c->d_kidx); cudaFree(c->d_frac);
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
+    cudaFree(c->d_twc); cudaFree(c->d_wsamp);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     HotTimer* t = timer_of(c);
     if (t) {
@@ -167,8 +178,9 @@ void psfr_destroy(psfr_ctx* c) {
 int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** out) {
     if (!out) return set_error(nullptr, PSFR_E_ARG, "out is NULL");
     *out = nullptr;
-    if (dim != kN)
-        return set_error(nullptr, PSFR_E_UNSUPPORTED, "dim=%d: this build supports dim=%d only", dim, kN);
+    if (dim != kNB && dim != 2 * kNB)
+        return set_error(nullptr, PSFR_E_UNSUPPORTED, "dim=%d: this build supports dim=%d and dim=%d only", dim, kNB,
+                         2 * kNB);
     if (max_planes < 1 || max_lambda < 1 || max_lambda > kMaxLambdaCap)
         return set_error(nullptr, PSFR_E_ARG, "max_planes=%d max_lambda=%d out of range", max_planes, max_lambda);
     int ndev = 0;
@@ -181,6 +193,12 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     c->device = device;
     c->max_planes = max_planes;
     c->max_lambda = max_lambda;
+    c->NF = dim / kNB;
+    c->N = dim;
+    c->NH = dim / 2;
+    c->rows = dim / 2 + 2;
+    c->pairs = c->rows / 2;
+    const size_t kN = c->N, kNH = c->NH, kRows = c->rows;
 #define CK(call)                         \
     do {                                 \
         int rc__ = (call);               \
@@ -208,6 +226,8 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
           psfr_destroy(c); return PSFR_E_UNSUPPORTED; }
     const size_t P = max_planes, LM = max_lambda;
     CK(dev_alloc(c, &c->d_tw, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
+    CK(dev_alloc(c, &c->d_twc, (size_t)kNB));
+    CK(dev_alloc(c, &c->d_wsamp, LM * 2 * kNS));
     CK(dev_alloc(c, &c->d_pup, (size_t)kNH * kNH));
     CK(dev_alloc(c, &c->d_otf, (size_t)kRows * kN));
     CK(dev_alloc(c, &c->d_geom, (size_t)3 * kAO * kAO));
@@ -239,6 +259,11 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     build_twiddles<kR3>(tw1, tw2);
     CKC(cudaMemcpy(c->d_tw, tw1.data(), tw1.size() * sizeof(double2), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_tw + tw1.size(), tw2.data(), tw2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    {
+        std::vector<double2> twc(kNB);
+        for (int k = 0; k < kNB; ++k) twc[k] = unit_root(k, c->N);
+        CKC(cudaMemcpy(c->d_twc, twc.data(), twc.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
     CK(run_build_otf(c, 0));
     CKC(cudaDeviceSynchronize());
 #undef CK
@@ -268,7 +293,7 @@ int psfr_psd(psfr_ctx* c, int ndraw, const double* draws, int ndir, const double
     if ((rc = upload_draws(c, ndraw, draws, ndir, s))) return rc;
     rc = run_psd(c, ndraw, ndir, ngs, s);
     if (rc) return rc;
-    if (out_psd) return from_device(c, out_psd, c->d_psd, (size_t)ndraw * ndir * kN * kN * sizeof(double), s);
+    if (out_psd) return from_device(c, out_psd, c->d_psd, (size_t)ndraw * ndir * c->N * c->N * sizeof(double), s);
     return PSFR_OK;
 }
 
@@ -278,7 +303,7 @@ int psfr_load_psd(psfr_ctx* c, int nplanes, const double* psd, void* stream) {
         return set_error(c, PSFR_E_CAPACITY, "nplanes=%d exceeds max_planes=%d", nplanes, c->max_planes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     PSFR_CUDA(c, cudaSetDevice(c->device));
-    int rc = to_device(c, c->d_psd, psd, (size_t)nplanes * kN * kN * sizeof(double), s);
+    int rc = to_device(c, c->d_psd, psd, (size_t)nplanes * c->N * c->N * sizeof(double), s);
     if (rc) return rc;
     c->planes_loaded = nplanes;
     c->planes_struct = 0;
@@ -303,11 +328,11 @@ int psfr_psd_to_psf(psfr_ctx* c, int plane, double lambda_m, double* out_psf, vo
     const double conv = 2 * 3.141592653589793 / (lambda_m * 1e9);
     // the PSD workspace of the LAST plane slot is not needed any more once D exists; write the
     // PSF into the transposed-buffer-free psd slot of this plane and copy it out
-    double* dst = is_device_ptr(out_psf) ? out_psf : c->d_psd + (size_t)plane * kN * kN;
+    double* dst = is_device_ptr(out_psf) ? out_psf : c->d_psd + (size_t)plane * c->N * c->N;
     int rc = run_full_psf(c, plane, 0.5 * (conv * conv), dst, s);
     if (rc) return rc;
     if (dst != out_psf) {
-        rc = from_device(c, out_psf, dst, (size_t)kN * kN * sizeof(double), s);
+        rc = from_device(c, out_psf, dst, (size_t)c->N * c->N * sizeof(double), s);
         if (rc) return rc;
         c->planes_loaded = 0;   // the PSD of that slot was overwritten
     }
@@ -521,14 +546,14 @@ int psfr_polyfit(psfr_ctx* c, int nseries, int nlam, const double* lambda_nm, in
 int psfr_get_otf(psfr_ctx* c, double* out) {
     if (!c || !out) return set_error(c, PSFR_E_ARG, "NULL argument");
     PSFR_CUDA(c, cudaSetDevice(c->device));
-    return from_device(c, out, c->d_otf, (size_t)kRows * kN * sizeof(double), 0);
+    return from_device(c, out, c->d_otf, (size_t)c->rows * c->N * sizeof(double), 0);
 }
 
 int psfr_get_structure_function(psfr_ctx* c, int plane, double* out) {
     if (!c || !out) return set_error(c, PSFR_E_ARG, "NULL argument");
     if (plane < 0 || plane >= c->planes_struct) return set_error(c, PSFR_E_STATE, "plane %d not available", plane);
     PSFR_CUDA(c, cudaSetDevice(c->device));
-    return from_device(c, out, c->d_dphi + (size_t)plane * kRows * kN, (size_t)kRows * kN * sizeof(double), 0);
+    return from_device(c, out, c->d_dphi + (size_t)plane * c->rows * c->N, (size_t)c->rows * c->N * sizeof(double), 0);
 }
 
 int psfr_debug_exp(psfr_ctx* c, int n, const double* x, double* y) {

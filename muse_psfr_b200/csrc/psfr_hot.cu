@@ -20,13 +20,18 @@
 
 namespace psfr {
 
-constexpr int kHotWarps = 8;   // consumer warps
-constexpr int kStages = 3;     // ring depth
-constexpr int kTile = 2 * kN;  // doubles per tile (two rows)
-constexpr uint32_t kTileBytes = kTile * sizeof(double);
-constexpr size_t kHotSmem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
-                            (size_t)kStages * 2 * kTileBytes + (size_t)kHotWarps * G::XBUF * sizeof(double);
-static_assert(kHotSmem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
+// Launch shape per grid size: the ring stage holds two rows of D and two of the telescope OTF
+// (4 N doubles), so dim 2560 affords two stages and four transform warps in 227 KB.
+template <int NF>
+struct HotCfg {
+    static constexpr int Warps = NF == 1 ? 8 : 4;    // consumer warps
+    static constexpr int Stages = NF == 1 ? 3 : 2;   // ring depth
+    static constexpr int Tile = 2 * Dim<NF>::N;      // doubles per tile (two rows)
+    static constexpr uint32_t TileBytes = Tile * sizeof(double);
+    static constexpr size_t Smem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
+                                   (size_t)Stages * 2 * TileBytes + (size_t)Warps * G::XBUF * sizeof(double);
+    static_assert(Smem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -70,14 +75,21 @@ struct HotParams {
     double2* Y;            // [nplanes][nlam][kNS][kRows]
     const double* clam;    // [nlam]
     const uint16_t* kidx;  // [nlam][kNS]
+    const double2* wsamp;  // [nlam][2][kNS] NF = 2: w_N^k of the sampled outputs and of their mirrors
     const double* dmin;    // [nplanes][kRows] smallest D of each row (finalize_dphi_kernel)
     int* next_item;        // work counter, zeroed before the launch
     double cut;            // OTF entries with c*D > cut (exp < e^-cut) are flushed to zero
     int nplanes, nlam;
 };
 
-__global__ void __launch_bounds__(kHotWarps * 32, 1)
+template <int NF>
+__global__ void __launch_bounds__(HotCfg<NF>::Warps * 32, 1)
 hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
+    using D = Dim<NF>;
+    using C = HotCfg<NF>;
+    constexpr int kStages = C::Stages, kHotWarps = C::Warps, kTile = C::Tile, kN = D::N, kRows = D::Rows,
+                  kPairs = D::Pairs;
+    constexpr uint32_t kTileBytes = C::TileBytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);   // per-stage count of warps done with it
@@ -158,45 +170,79 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     continue;
                 }
                 const double negc = -cl, ncut = -p.cut;
-                double2 v[40];
-                // two slots (= four independent exp chains) per basic block
-#pragma unroll
-                for (int i = 0; i < 40; i += 2) {
-                    const int n0 = slot_n(i, lane), n1 = slot_n(i + 1, lane);
-                    const double ta = sT[n0], tb = sT[kN + n0], tc = sT[n1], td = sT[kN + n1];
-                    const double xa = negc * sD[n0], xb_ = negc * sD[kN + n0];
-                    const double xc = negc * sD[n1], xd = negc * sD[kN + n1];
-                    // outside the pupil-autocorrelation support the OTF is exactly zero; below the
-                    // underflow cut it is flushed to zero
-                    const bool dead = ((ta == 0.0) | (xa < ncut)) & ((tb == 0.0) | (xb_ < ncut)) &
-                                      ((tc == 0.0) | (xc < ncut)) & ((td == 0.0) | (xd < ncut));
-                    if (__all_sync(0xffffffffu, dead)) {
-                        v[i] = make_double2(0.0, 0.0);
-                        v[i + 1] = make_double2(0.0, 0.0);
-                    } else {
-                        const double ea = fast_exp(xa), eb = fast_exp(xb_);
-                        const double ec = fast_exp(xc), ed = fast_exp(xd);
-                        v[i] = make_double2(ea * ta, eb * tb);
-                        v[i + 1] = make_double2(ec * tc, ed * td);
-                    }
-                }
-                warp_fft<kR3>(v, xb, tw1, tw2, lane);
-                // gather the sampled frequencies kA and their mirrors kB = -kA
+                // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
                 const uint16_t* kx = p.kidx + (size_t)lam * kNS;
-                double2 za[3], zb[3];
                 int ka[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
+                double2 za[3], zb[3];   // X[kA], X[kB] accumulated over the NF interleaved sub-sequences
+#pragma unroll 1
+                for (int sub = 0; sub < NF; ++sub) {
+                    double2 v[40];
+                    // two slots (= four independent exp chains) per basic block
 #pragma unroll
-                for (int cpt = 0; cpt < 2; ++cpt) {
-                    fft_dump<kR3>(v, xb, lane, cpt);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        comp_set(za[i], cpt, xb[nat_addr(ka[i])]);
-                        comp_set(zb[i], cpt, xb[nat_addr((kN - ka[i]) % kN)]);
+                    for (int i = 0; i < 40; i += 2) {
+                        const int n0 = slot_e<NF>(i, lane, sub), n1 = slot_e<NF>(i + 1, lane, sub);
+                        const double ta = sT[n0], tb = sT[kN + n0], tc = sT[n1], td = sT[kN + n1];
+                        const double xa = negc * sD[n0], xb_ = negc * sD[kN + n0];
+                        const double xc = negc * sD[n1], xd = negc * sD[kN + n1];
+                        // outside the pupil-autocorrelation support the OTF is exactly zero; below
+                        // the underflow cut it is flushed to zero
+                        const bool dead = ((ta == 0.0) | (xa < ncut)) & ((tb == 0.0) | (xb_ < ncut)) &
+                                          ((tc == 0.0) | (xc < ncut)) & ((td == 0.0) | (xd < ncut));
+                        if (__all_sync(0xffffffffu, dead)) {
+                            v[i] = make_double2(0.0, 0.0);
+                            v[i + 1] = make_double2(0.0, 0.0);
+                        } else {
+                            const double ea = fast_exp(xa), eb = fast_exp(xb_);
+                            const double ec = fast_exp(xc), ed = fast_exp(xd);
+                            v[i] = make_double2(ea * ta, eb * tb);
+                            v[i + 1] = make_double2(ec * tc, ed * td);
+                        }
                     }
-                    __syncwarp();
+                    warp_fft<kR3>(v, xb, tw1, tw2, lane);
+                    double2 fa[3], fb[3];
+#pragma unroll
+                    for (int cpt = 0; cpt < 2; ++cpt) {
+                        fft_dump<kR3>(v, xb, lane, cpt);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            comp_set(fa[i], cpt, xb[nat_addr(ka[i] % kNB)]);
+                            comp_set(fb[i], cpt, xb[nat_addr(((kN - ka[i]) % kN) % kNB)]);
+                        }
+                        __syncwarp();
+                    }
+                    if (NF == 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            za[i] = fa[i];
+                            zb[i] = fb[i];
+                        }
+                    } else if (sub == 0) {
+                        // park F0 in the output slots (L2-resident) instead of 12 more live registers
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int y = lane + 32 * i;
+                            if (y < kNS) {
+                                double2* o = out + (size_t)y * kRows;
+                                o[0] = fa[i];
+                                o[1] = fb[i];
+                            }
+                        }
+                    } else {
+                        // X[k] = F0[k mod 1280] + w_N^k F1[k mod 1280]
+                        const double2* ws = p.wsamp + (size_t)lam * 2 * kNS;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int y = lane + 32 * i;
+                            if (y < kNS) {
+                                const double2* o = out + (size_t)y * kRows;
+                                za[i] = cadd(o[0], cmul(fa[i], __ldg(ws + y)));
+                                zb[i] = cadd(o[1], cmul(fb[i], __ldg(ws + kNS + y)));
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -227,26 +273,28 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
 // ---------------- pruned column pass
 // line f = ((draw*nlam + lam)*40 + m): sampled rows 2m, 2m+1 of that PSF, summed over the
 // ndir planes of the draw, Hermitian-extended along the half-plane row index.
+template <int NF>
 struct LoadSampledPair {
-    const double2* Y;  // [nplanes][nlam][kNS][kRows]
+    using D = Dim<NF>;
+    const double2* Y;  // [nplanes][nlam][kNS][Rows]
     int nlam, ndir;
-    __device__ void operator()(int f, int lane, double2* v) const {
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
         const int m = f % (kNS / 2), img = f / (kNS / 2);
         const int lam = img % nlam, draw = img / nlam;
 #pragma unroll
         for (int i = 0; i < 40; ++i) v[i] = make_double2(0.0, 0.0);
         for (int d = 0; d < ndir; ++d) {
-            const double2* c1 = Y + (((size_t)(draw * ndir + d) * nlam + lam) * kNS + 2 * m) * kRows;
-            const double2* c2 = c1 + kRows;
+            const double2* c1 = Y + (((size_t)(draw * ndir + d) * nlam + lam) * kNS + 2 * m) * D::Rows;
+            const double2* c2 = c1 + D::Rows;
 #pragma unroll
             for (int i = 0; i < 40; ++i) {
-                const int n = slot_n(i, lane);
-                if (n <= kNH) {
+                const int n = slot_e<NF>(i, lane, sub);
+                if (n <= D::NH) {
                     const double2 r1 = __ldg(c1 + n), r2 = __ldg(c2 + n);
                     v[i].x += r1.x - r2.y;
                     v[i].y += r1.y + r2.x;
                 } else {
-                    const double2 r1 = __ldg(c1 + (kN - n)), r2 = __ldg(c2 + (kN - n));
+                    const double2 r1 = __ldg(c1 + (D::N - n)), r2 = __ldg(c2 + (D::N - n));
                     v[i].x += r1.x + r2.y;
                     v[i].y += r2.x - r1.y;
                 }
@@ -256,6 +304,7 @@ struct LoadSampledPair {
 };
 
 // samples S[img][i][j] = scale * (-1)^(X_i + Y_j) * F[xi_i, eta_j]
+template <int NF>
 struct StoreSamples {
     double* S;             // [nimg][kNS][kNS]
     const uint16_t* kidx;  // [nlam][kNS]
@@ -272,7 +321,7 @@ struct StoreSamples {
             const int j = lane + 32 * i;
             if (j < kNS) {
                 const int kj = __ldg(kx + j);
-                const double2 z = nat_get(xb, kj);
+                const double2 z = nat_get<NF>(xb, kj);
                 o[j] = (((k1 + kj) & 1) ? -scale : scale) * z.x;
                 o[kNS + j] = (((k2 + kj) & 1) ? -scale : scale) * z.y;
             }
@@ -280,22 +329,25 @@ struct StoreSamples {
     }
 };
 
-int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
+template <int NF>
+static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
+    using D = Dim<NF>;
+    using C = HotCfg<NF>;
     static bool attr_set = false;
     if (!attr_set) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(hot_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kHotSmem));
+        PSFR_CUDA(c, cudaFuncSetAttribute(hot_rows_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)C::Smem));
         attr_set = true;
     }
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_dmin, c->d_counter,
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_counter,
                 c->exp_cut, nplanes, nlam};
     int grid = c->sm_count;
-    if (grid > nplanes * kPairs) grid = nplanes * kPairs;
+    if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
     int rc = hot_event(c, 0, s);
     if (rc) return rc;
-    hot_rows_kernel<<<grid, kHotWarps * 32, kHotSmem, s>>>(p, c->d_tw);
+    hot_rows_kernel<NF><<<grid, C::Warps * 32, C::Smem, s>>>(p, c->d_tw);
     PSFR_LAUNCH_CHECK(c);
     if ((rc = hot_event(c, 1, s))) return rc;
     c->hot_launches += 1;
@@ -303,8 +355,12 @@ int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
     // inverse transform); psf_muse averages the directions.
     const double scale = 1.0 / ndir;
-    return launch_pass(c, LoadSampledPair{c->d_ybuf, nlam, ndir},
-                       StoreSamples{c->d_samp, c->d_kidx, nlam, scale}, ndraw * nlam * (kNS / 2), s);
+    return launch_pass<NF>(c, LoadSampledPair<NF>{c->d_ybuf, nlam, ndir},
+                           StoreSamples<NF>{c->d_samp, c->d_kidx, nlam, scale}, ndraw * nlam * (kNS / 2), s);
+}
+
+int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
+    return c->NF == 1 ? pruned_psf_t<1>(c, ndraw, ndir, nlam, s) : pruned_psf_t<2>(c, ndraw, ndir, nlam, s);
 }
 
 }  // namespace psfr

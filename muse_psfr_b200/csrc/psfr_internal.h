@@ -7,11 +7,19 @@
 
 namespace psfr {
 
-constexpr int kR3 = 20;                 // N = 64*R3 = 1280
-constexpr int kN = 64 * kR3;
-constexpr int kNH = kN / 2;             // 640
-constexpr int kRows = kNH + 2;          // half-plane rows 0..640 plus one zero pad row
-constexpr int kPairs = kRows / 2;       // 321 row pairs
+constexpr int kR3 = 20;                 // the warp transform has length 64*R3 = 1280
+constexpr int kNB = 64 * kR3;           // base line length 1280
+// Grid sizes: N = NF * 1280 with NF = 1 (dim 1280, compute_psf) or NF = 2 (dim 2560, BASELINE
+// config 5).  A length-N line is NF interleaved 1280-point warp transforms plus one radix-NF
+// combine (decimation in time).
+template <int NF>
+struct Dim {
+    static_assert(NF == 1 || NF == 2, "dim must be 1280 or 2560");
+    static constexpr int N = NF * kNB;
+    static constexpr int NH = N / 2;
+    static constexpr int Rows = NH + 2;      // half-plane rows 0..N/2 plus one zero pad row
+    static constexpr int Pairs = Rows / 2;   // row pairs
+};
 constexpr int kAO = PSFR_AO_DIM;        // 80
 constexpr int kPSF = PSFR_PSF_DIM;      // 40
 constexpr int kNS = 2 * kPSF;           // 80 sampled rows / columns per PSF
@@ -31,7 +39,11 @@ inline int misc_size(int max_planes) { return kMiscCentre + 2 * max_planes + 64;
 
 struct Ctx {
     int device = 0;
-    int N = kN;
+    int NF = 1;                  // N / 1280
+    int N = kNB;                 // PSD grid size (dim)
+    int NH = kNB / 2;            // N / 2
+    int rows = kNB / 2 + 2;      // half-plane rows incl. the zero pad row
+    int pairs = kNB / 4 + 1;     // row pairs
     int max_planes = 0;
     int max_lambda = 0;
     int sm_count = 148;
@@ -42,16 +54,18 @@ struct Ctx {
     double pup_sum = 0;
 
     double2* d_tw = nullptr;     // twiddles: TW1 then TW2
+    double2* d_twc = nullptr;    // [1280] combine twiddles exp(+2 pi i k / N) (NF = 2)
     double* d_pup = nullptr;     // [N/2][N/2] pupil as doubles
-    double* d_otf = nullptr;     // [kRows][N] telescope OTF half-plane (centred, pad row zero)
+    double* d_otf = nullptr;     // [rows][N] telescope OTF half-plane (centred, pad row zero)
     double* d_geom = nullptr;    // f, f_x, f_y: 3 x 80 x 80
     double* d_psd = nullptr;     // [max_planes][N][N]
-    double2* d_bt = nullptr;     // [max_planes][N][kRows] transposed row-pass output (full mode)
-    double* d_dphi = nullptr;    // [max_planes][kRows][N] structure function (transposed half-plane)
-    double* d_dmin = nullptr;    // [max_planes][kRows] smallest structure-function value of each row
+    double2* d_bt = nullptr;     // [max_planes][N][rows] transposed row-pass output (full mode)
+    double* d_dphi = nullptr;    // [max_planes][rows][N] structure function (transposed half-plane)
+    double* d_dmin = nullptr;    // [max_planes][rows] smallest structure-function value of each row
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
-    double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][kRows] pruned row-pass output
+    double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
+    double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples
     double* d_ao = nullptr;      // [max_planes][80][80] AO-zone PSD (centred, reference orientation)
     double* d_draws = nullptr;   // [max_planes][PSFR_DRAW_NPAR]

@@ -7,29 +7,32 @@
 //   init     : pupil -> telescope OTF               (psfrec.py:784-790)
 // A 2-D transform is two passes; the first writes its output transposed in 32-byte
 // sectors, the second reads contiguous lines again, so no stand-alone transpose exists.
+// Everything is templated on NF = dim / 1280 (see Dim<NF>, pass_kernel.cuh).
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 
 namespace psfr {
 
 // ------------------------------------------------------------------ loaders
-// E = (P + P reflected)/2 on rows (2rp, 2rp+1) of plane f / kPairs: real-even input whose
+// E = (P + P reflected)/2 on rows (2rp, 2rp+1) of plane f / Pairs: real-even input whose
 // transform is Re of the transform of P (psfrec.py:718,721 keeps only bg.real).
+template <int NF>
 struct LoadEvenRows {
+    using D = Dim<NF>;
     const double* P;  // [nplanes][N][N]
-    __device__ void operator()(int f, int lane, double2* v) const {
-        const int plane = f / kPairs, rp = f % kPairs;
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
+        const int plane = f / D::Pairs, rp = f % D::Pairs;
         const int a1 = 2 * rp, a2 = a1 + 1;
-        const double* base = P + (size_t)plane * kN * kN;
-        const double* r1 = base + (size_t)a1 * kN;
-        const double* r1m = base + (size_t)((kN - a1) % kN) * kN;
-        const bool ok2 = a2 <= kNH;
-        const double* r2 = base + (size_t)(ok2 ? a2 : 0) * kN;
-        const double* r2m = base + (size_t)(ok2 ? (kN - a2) : 0) * kN;
+        const double* base = P + (size_t)plane * D::N * D::N;
+        const double* r1 = base + (size_t)a1 * D::N;
+        const double* r1m = base + (size_t)((D::N - a1) % D::N) * D::N;
+        const bool ok2 = a2 <= D::NH;
+        const double* r2 = base + (size_t)(ok2 ? a2 : 0) * D::N;
+        const double* r2m = base + (size_t)(ok2 ? (D::N - a2) : 0) * D::N;
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
-            const int n = slot_n(i, lane);
-            const int nm = (kN - n) % kN;
+            const int n = slot_e<NF>(i, lane, sub);
+            const int nm = (D::N - n) % D::N;
             const double e1 = 0.5 * (__ldg(r1 + n) + __ldg(r1m + nm));
             const double e2 = ok2 ? 0.5 * (__ldg(r2 + n) + __ldg(r2m + nm)) : 0.0;
             v[i] = make_double2(e1, e2);
@@ -37,32 +40,36 @@ struct LoadEvenRows {
     }
 };
 
-// rows (2rp, 2rp+1) of exp(-c D) * OTF on the transposed half-plane (psfrec.py:793-797)
+// rows (2f, 2f+1) of exp(-c D) * OTF on the transposed half-plane (psfrec.py:793-797)
+template <int NF>
 struct LoadOtfRows {
-    const double* D;   // [kRows][N] of the selected plane
-    const double* T;   // [kRows][N]
+    using D_ = Dim<NF>;
+    const double* D;   // [Rows][N] of the selected plane
+    const double* T;   // [Rows][N]
     double c;
-    __device__ void operator()(int f, int lane, double2* v) const {
-        const double* d1 = D + (size_t)(2 * f) * kN;
-        const double* t1 = T + (size_t)(2 * f) * kN;
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
+        const double* d1 = D + (size_t)(2 * f) * D_::N;
+        const double* t1 = T + (size_t)(2 * f) * D_::N;
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
-            const int n = slot_n(i, lane);
+            const int n = slot_e<NF>(i, lane, sub);
             v[i] = make_double2(fast_exp(-c * __ldg(d1 + n)) * __ldg(t1 + n),
-                                fast_exp(-c * __ldg(d1 + kN + n)) * __ldg(t1 + kN + n));
+                                fast_exp(-c * __ldg(d1 + D_::N + n)) * __ldg(t1 + D_::N + n));
         }
     }
 };
 
 // pupil rows (2f, 2f+1), zero-padded to N columns (psfrec.py:784-787)
+template <int NF>
 struct LoadPupilRows {
+    using D = Dim<NF>;
     const double* pup;  // [N/2][N/2]
-    __device__ void operator()(int f, int lane, double2* v) const {
-        const double* p1 = pup + (size_t)(2 * f) * kNH;
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
+        const double* p1 = pup + (size_t)(2 * f) * D::NH;
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
-            const int n = slot_n(i, lane);
-            v[i] = n < kNH ? make_double2(__ldg(p1 + n), __ldg(p1 + kNH + n)) : make_double2(0., 0.);
+            const int n = slot_e<NF>(i, lane, sub);
+            v[i] = n < D::NH ? make_double2(__ldg(p1 + n), __ldg(p1 + D::NH + n)) : make_double2(0., 0.);
         }
     }
 };
@@ -71,23 +78,25 @@ struct LoadPupilRows {
 // y(2m), y(2m+1) with y(a) = (a + N/2) % N and forms R[.,y1] + i R[.,y2] over all N rows,
 // R[N-a] = conj(R[a]).  The transform of that line is real-in-two-halves: Re -> output
 // row 2m, Im -> output row 2m+1.
+template <int NF>
 struct LoadHermitianPair {
-    const double2* Bt;  // [nplanes][N][kRows]
+    using D = Dim<NF>;
+    const double2* Bt;  // [nplanes][N][Rows]
     int npair;          // pairs per plane
     int last_valid;     // largest valid output row (the partner of an invalid row is duplicated)
-    __device__ void operator()(int f, int lane, double2* v) const {
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
         const int plane = f / npair, m = f % npair;
         const int o1 = 2 * m, o2 = (2 * m + 1 <= last_valid) ? 2 * m + 1 : o1;
-        const double2* c1 = Bt + ((size_t)plane * kN + (o1 + kNH) % kN) * kRows;
-        const double2* c2 = Bt + ((size_t)plane * kN + (o2 + kNH) % kN) * kRows;
+        const double2* c1 = Bt + ((size_t)plane * D::N + (o1 + D::NH) % D::N) * D::Rows;
+        const double2* c2 = Bt + ((size_t)plane * D::N + (o2 + D::NH) % D::N) * D::Rows;
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
-            const int n = slot_n(i, lane);
-            if (n <= kNH) {
+            const int n = slot_e<NF>(i, lane, sub);
+            if (n <= D::NH) {
                 const double2 r1 = __ldg(c1 + n), r2 = __ldg(c2 + n);
                 v[i] = make_double2(r1.x - r2.y, r1.y + r2.x);
             } else {
-                const double2 r1 = __ldg(c1 + (kN - n)), r2 = __ldg(c2 + (kN - n));
+                const double2 r1 = __ldg(c1 + (D::N - n)), r2 = __ldg(c2 + (D::N - n));
                 v[i] = make_double2(r1.x + r2.y, r2.x - r1.y);
             }
         }
@@ -95,14 +104,16 @@ struct LoadHermitianPair {
 };
 
 // single complex column y = f, rows >= nrows are zero (forward transform of the padded pupil)
+template <int NF>
 struct LoadColumnPadded {
-    const double2* Bt;  // [N][kRows]
+    using D = Dim<NF>;
+    const double2* Bt;  // [N][Rows]
     int nrows;
-    __device__ void operator()(int f, int lane, double2* v) const {
-        const double2* c1 = Bt + (size_t)f * kRows;
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
+        const double2* c1 = Bt + (size_t)f * D::Rows;
 #pragma unroll
         for (int i = 0; i < 40; ++i) {
-            const int n = slot_n(i, lane);
+            const int n = slot_e<NF>(i, lane, sub);
             v[i] = n < nrows ? __ldg(c1 + n) : make_double2(0., 0.);
         }
     }
@@ -110,17 +121,19 @@ struct LoadColumnPadded {
 
 // ------------------------------------------------------------------ storers
 // untangle the two real lines and write them transposed: Bt[plane][y][2rp], [2rp+1]
+template <int NF>
 struct StoreTransposedPair {
-    double2* Bt;  // [nplanes][N][kRows]
+    using D = Dim<NF>;
+    double2* Bt;  // [nplanes][N][Rows]
     int npair;
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / npair, rp = f % npair;
-        double2* out = Bt + (size_t)plane * kN * kRows + 2 * rp;
+        double2* out = Bt + (size_t)plane * D::N * D::Rows + 2 * rp;
 #pragma unroll 4
-        for (int i = 0; i < 40; ++i) {
+        for (int i = 0; i < 40 * NF; ++i) {
             const int y = lane + 32 * i;
-            const double2 za = nat_get(xb, y), zb = nat_get(xb, (kN - y) % kN);
-            double2* o = out + (size_t)y * kRows;
+            const double2 za = nat_get<NF>(xb, y), zb = nat_get<NF>(xb, (D::N - y) % D::N);
+            double2* o = out + (size_t)y * D::Rows;
             o[0] = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
             o[1] = make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x));
         }
@@ -130,7 +143,9 @@ struct StoreTransposedPair {
 // Re -> row 2m, Im -> row 2m+1 of out[plane][nrows_out][N], column b = (x + N/2) % N,
 // value * scale * (-1)^(row + b).  The sign alternation is the output-side image of an input
 // that was stored centred (fftshift-ed); `alternate` = 0 for an input in natural FFT order.
+template <int NF>
 struct StoreRealRows {
+    using D = Dim<NF>;
     double* out;
     int npair, nrows_out, last_valid;
     double scale;
@@ -138,68 +153,70 @@ struct StoreRealRows {
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / npair, m = f % npair;
         const int o1 = 2 * m, o2 = o1 + 1;
-        double* r1 = out + ((size_t)plane * nrows_out + o1) * kN;
+        double* r1 = out + ((size_t)plane * nrows_out + o1) * D::N;
         const bool ok2 = o2 <= last_valid;
 #pragma unroll 4
-        for (int i = 0; i < 40; ++i) {
+        for (int i = 0; i < 40 * NF; ++i) {
             const int b = lane + 32 * i;
-            const double2 z = nat_get(xb, (b + kNH) % kN);
+            const double2 z = nat_get<NF>(xb, (b + D::NH) % D::N);
             const double s1 = (alternate && ((o1 + b) & 1)) ? -scale : scale;
             r1[b] = s1 * z.x;
-            if (ok2) r1[kN + b] = (alternate ? -s1 : s1) * z.y;
+            if (ok2) r1[D::N + b] = (alternate ? -s1 : s1) * z.y;
         }
     }
 };
 
 // |Z[x]|^2 -> out[y = f][x]
+template <int NF>
 struct StoreAbs2 {
+    using D = Dim<NF>;
     double* out;  // [N][N]
     __device__ void operator()(int f, int lane, const double* xb) const {
-        double* r = out + (size_t)f * kN;
+        double* r = out + (size_t)f * D::N;
 #pragma unroll 4
-        for (int i = 0; i < 40; ++i) {
+        for (int i = 0; i < 40 * NF; ++i) {
             const int x = lane + 32 * i;
-            const double2 z = nat_get(xb, x);
+            const double2 z = nat_get<NF>(xb, x);
             r[x] = z.x * z.x + z.y * z.y;
         }
     }
 };
 
 // ------------------------------------------------------------------ small elementwise kernels
-__global__ void pupil_kernel(double* pup, double radius, double oc) {
+__global__ void pupil_kernel(double* pup, int nh, double radius, double oc) {
     // pupil_mask(N/4, N/2, oc) (psfrec.py:190-203): rho = hypot(x-c, y-c)/radius
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kNH * kNH) return;
-    const int y = idx / kNH, x = idx % kNH;
-    const double cc = (kNH - 1) / 2.0;
+    if (idx >= nh * nh) return;
+    const int y = idx / nh, x = idx % nh;
+    const double cc = (nh - 1) / 2.0;
     const double rho = hypot(y - cc, x - cc) / radius;
     pup[idx] = (rho < 1.0 && rho >= oc) ? 1.0 : 0.0;
 }
 
 // T = rint(autocorrelation counts) / (N^2 * sum(pupil)), pad row zero
-__global__ void finalize_otf_kernel(double* t, double inv_norm) {
+__global__ void finalize_otf_kernel(double* t, size_t live, size_t total, double inv_norm) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)kRows * kN) return;
-    t[idx] = (idx >= (size_t)(kNH + 1) * kN) ? 0.0 : rint(t[idx]) * inv_norm;
+    if (idx >= total) return;
+    t[idx] = (idx >= live) ? 0.0 : rint(t[idx]) * inv_norm;
 }
 
 // ------------------------------------------------------------------ drivers
-__global__ void stash_centre_kernel(const double* d, double* centre, int nplanes) {
+__global__ void stash_centre_kernel(const double* d, double* centre, int nplanes, size_t per, size_t at) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < nplanes) centre[p] = d[(size_t)p * kRows * kN + (size_t)kNH * kN + kNH];
+    if (p < nplanes) centre[p] = d[(size_t)p * per + at];
 }
 
 // D[a][b] = Draw[N/2][N/2] - Draw[a][b], pad row zero (psfrec.py:721: 2*(bg[0,0] - bg)); one
 // block per row, which also records the smallest D of the row for the underflow cut of stage B
 __global__ void __launch_bounds__(256)
-finalize_dphi_kernel(double* d, const double* centre, double* dmin) {
+finalize_dphi_kernel(double* d, const double* centre, double* dmin, int n, int rows) {
     __shared__ double red[8];
-    const int row = blockIdx.x % kRows, plane = blockIdx.x / kRows;
-    double* r = d + ((size_t)plane * kRows + row) * kN;
+    const int row = blockIdx.x % rows, plane = blockIdx.x / rows;
+    double* r = d + ((size_t)plane * rows + row) * n;
     const double c0 = centre[plane];
     double m = 1e300;
-    for (int b = threadIdx.x; b < kN; b += blockDim.x) {
-        const double v = (row > kNH) ? 0.0 : c0 - r[b];
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+        const double v = (row > n / 2) ? 0.0 : c0 - r[b];
         r[b] = v;
         m = fmin(m, v);
     }
@@ -209,40 +226,55 @@ finalize_dphi_kernel(double* d, const double* centre, double* dmin) {
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) m = fmin(m, red[w]);
-        dmin[(size_t)plane * kRows + row] = m;
+        dmin[(size_t)plane * rows + row] = m;
     }
 }
 
 static int launch_finalize_dphi(Ctx* c, int nplanes, cudaStream_t s) {
     double* centre = c->d_misc + kMiscCentre;  // scratch area reserved for plane centres
-    stash_centre_kernel<<<(nplanes + 127) / 128, 128, 0, s>>>(c->d_dphi, centre, nplanes);
+    stash_centre_kernel<<<(nplanes + 127) / 128, 128, 0, s>>>(c->d_dphi, centre, nplanes, (size_t)c->rows * c->N,
+                                                              (size_t)c->NH * c->N + c->NH);
     PSFR_LAUNCH_CHECK(c);
-    finalize_dphi_kernel<<<nplanes * kRows, 256, 0, s>>>(c->d_dphi, centre, c->d_dmin);
+    finalize_dphi_kernel<<<nplanes * c->rows, 256, 0, s>>>(c->d_dphi, centre, c->d_dmin, c->N, c->rows);
     PSFR_LAUNCH_CHECK(c);
     c->planes_struct = nplanes;
     return PSFR_OK;
 }
 
-int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
+template <int NF>
+static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s) {
+    using D = Dim<NF>;
     // pass 1: rows of the even part of the PSD -> transposed half spectrum
-    int rc = launch_pass(c, LoadEvenRows{c->d_psd}, StoreTransposedPair{c->d_bt, kPairs}, nplanes * kPairs, s);
+    int rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
+                             nplanes * D::Pairs, s);
     if (rc) return rc;
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
     const double L = 16.0;
-    rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
-                     StoreRealRows{c->d_dphi, kPairs, kRows, kNH, 2.0 / (L * L), 1}, nplanes * kPairs, s);
+    rc = launch_pass<NF>(c, LoadHermitianPair<NF>{c->d_bt, D::Pairs, D::NH},
+                         StoreRealRows<NF>{c->d_dphi, D::Pairs, D::Rows, D::NH, 2.0 / (L * L), 1}, nplanes * D::Pairs, s);
     if (rc) return rc;
     return launch_finalize_dphi(c, nplanes, s);
 }
 
-int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s) {
-    const double* D = c->d_dphi + (size_t)plane * kRows * kN;
-    int rc = launch_pass(c, LoadOtfRows{D, c->d_otf, clam}, StoreTransposedPair{c->d_bt, kPairs}, kPairs, s);
+int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
+    return c->NF == 1 ? structure_function_t<1>(c, nplanes, s) : structure_function_t<2>(c, nplanes, s);
+}
+
+template <int NF>
+static int full_psf_t(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s) {
+    using D = Dim<NF>;
+    const double* Dp = c->d_dphi + (size_t)plane * D::Rows * D::N;
+    int rc = launch_pass<NF>(c, LoadOtfRows<NF>{Dp, c->d_otf, clam}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
+                             D::Pairs, s);
     if (rc) return rc;
     // psf/psf.sum(): the sum of the raw PSF is the OTF at the origin = 1/N^2 exactly (T centre);
     // the unnormalised inverse transform carries 1/N^2 as well, so the two cancel.
-    return launch_pass(c, LoadHermitianPair{c->d_bt, kNH, kN - 1},
-                       StoreRealRows{out_dev, kNH, kN, kN - 1, 1.0, 1}, kNH, s);
+    return launch_pass<NF>(c, LoadHermitianPair<NF>{c->d_bt, D::NH, D::N - 1},
+                           StoreRealRows<NF>{out_dev, D::NH, D::N, D::N - 1, 1.0, 1}, D::NH, s);
+}
+
+int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s) {
+    return c->NF == 1 ? full_psf_t<1>(c, plane, clam, out_dev, s) : full_psf_t<2>(c, plane, clam, out_dev, s);
 }
 
 __global__ void debug_exp_kernel(const double* x, double* y, int n) {
@@ -256,30 +288,35 @@ int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_
     return PSFR_OK;
 }
 
-int run_build_otf(Ctx* c, cudaStream_t s) {
-    pupil_kernel<<<(kNH * kNH + 255) / 256, 256, 0, s>>>(c->d_pup, kN / 4.0, 0.14);
+template <int NF>
+static int build_otf_t(Ctx* c, cudaStream_t s) {
+    using D = Dim<NF>;
+    pupil_kernel<<<(D::NH * D::NH + 255) / 256, 256, 0, s>>>(c->d_pup, D::NH, D::N / 4.0, 0.14);
     PSFR_LAUNCH_CHECK(c);
     // forward transform of the zero-padded pupil: rows (real pairs) then complex columns -> |.|^2
-    int rc = launch_pass(c, LoadPupilRows{c->d_pup}, StoreTransposedPair{c->d_bt, kNH / 2}, kNH / 2, s);
+    int rc = launch_pass<NF>(c, LoadPupilRows<NF>{c->d_pup}, StoreTransposedPair<NF>{c->d_bt, D::NH / 2}, D::NH / 2, s);
     if (rc) return rc;
-    rc = launch_pass(c, LoadColumnPadded{c->d_bt, kNH}, StoreAbs2{c->d_psd}, kN, s);
+    rc = launch_pass<NF>(c, LoadColumnPadded<NF>{c->d_bt, D::NH}, StoreAbs2<NF>{c->d_psd}, D::N, s);
     if (rc) return rc;
     // inverse transform of |P^|^2 (real, even): N^2 x the pupil autocorrelation, centred
-    rc = launch_pass(c, LoadEvenRows{c->d_psd}, StoreTransposedPair{c->d_bt, kPairs}, kPairs, s);
+    rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs}, D::Pairs, s);
     if (rc) return rc;
-    rc = launch_pass(c, LoadHermitianPair{c->d_bt, kPairs, kNH},
-                     StoreRealRows{c->d_otf, kPairs, kRows, kNH, 1.0 / ((double)kN * kN), 0}, kPairs, s);
+    rc = launch_pass<NF>(c, LoadHermitianPair<NF>{c->d_bt, D::Pairs, D::NH},
+                         StoreRealRows<NF>{c->d_otf, D::Pairs, D::Rows, D::NH, 1.0 / ((double)D::N * D::N), 0}, D::Pairs, s);
     if (rc) return rc;
     double centre = 0;
-    PSFR_CUDA(c, cudaMemcpyAsync(&centre, c->d_otf + (size_t)kNH * kN + kNH, sizeof(double),
+    PSFR_CUDA(c, cudaMemcpyAsync(&centre, c->d_otf + (size_t)D::NH * D::N + D::NH, sizeof(double),
                                  cudaMemcpyDeviceToHost, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));
     c->pup_sum = rint(centre);
     if (!(c->pup_sum > 0)) return set_error(c, PSFR_E_CUDA, "telescope OTF init failed (pupil sum %g)", centre);
-    finalize_otf_kernel<<<(kRows * kN + 255) / 256, 256, 0, s>>>(
-        c->d_otf, 1.0 / ((double)kN * kN * c->pup_sum));
+    const size_t total = (size_t)D::Rows * D::N;
+    finalize_otf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        c->d_otf, (size_t)(D::NH + 1) * D::N, total, 1.0 / ((double)D::N * D::N * c->pup_sum));
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }
+
+int run_build_otf(Ctx* c, cudaStream_t s) { return c->NF == 1 ? build_otf_t<1>(c, s) : build_otf_t<2>(c, s); }
 
 }  // namespace psfr

@@ -114,8 +114,9 @@ __global__ void ao_zone_kernel(PsdParams p) {
 }
 
 __global__ void psd_fill_kernel(const double* __restrict__ draws, const double* __restrict__ ao,
-                                double* __restrict__ psd, int ndir, double scale2) {
+                                double* __restrict__ psd, int ndir, double scale2, int kN) {
     // one thread per quadrant cell (a, b), a, b in [0, N/2): fit(a,b) = fit(N-1-a, b) = ...
+    const int kNH = kN / 2;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = blockIdx.y;
     const int plane = blockIdx.z;
@@ -147,8 +148,8 @@ int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s) {
     ao_zone_kernel<<<g1, 128, 0, s>>>(p);
     PSFR_LAUNCH_CHECK(c);
     const double k = 0.5 * 1000 / (2 * 3.141592653589793);
-    dim3 g2((kNH + 127) / 128, kNH, nplanes);
-    psd_fill_kernel<<<g2, 128, 0, s>>>(c->d_draws, c->d_ao, c->d_psd, ndir, k * k);
+    dim3 g2((c->NH + 127) / 128, c->NH, nplanes);
+    psd_fill_kernel<<<g2, 128, 0, s>>>(c->d_draws, c->d_ao, c->d_psd, ndir, k * k, c->N);
     PSFR_LAUNCH_CHECK(c);
     c->planes_loaded = nplanes;
     c->planes_struct = 0;

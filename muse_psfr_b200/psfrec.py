@@ -22,7 +22,8 @@ MAX_L0 = 30
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _WIND_DIR = np.array([0.628163, -0.326497])      # psfrec.py:66
-_DIM = 1280                                      # psfrec.py:955
+_DIM = 1280                                      # psfrec.py:955 (compute_psf's fixed grid)
+_DIMS = (1280, 2560)                             # grids the CUDA library is built for
 _CONTEXTS = {}
 _DEFAULT_DEVICE = [None]
 
@@ -39,19 +40,28 @@ def _device():
     return _DEFAULT_DEVICE[0]
 
 
-def get_context(max_planes=16, max_lambda=35, device=None):
-    """Context cache: one context per device, grown when a call needs more capacity."""
+def _check_dim(dim):
+    if int(dim) not in _DIMS:
+        raise NotImplementedError('this build supports dim in %s only (got %r)' % (_DIMS, dim))
+    return int(dim)
+
+
+def get_context(max_planes=None, max_lambda=35, device=None, dim=_DIM):
+    """Context cache: one context per (device, dim), grown when a call needs more capacity."""
     device = _device() if device is None else int(device)
-    ctx = _CONTEXTS.get(device)
+    dim = _check_dim(dim)
+    if max_planes is None:
+        max_planes = 16 if dim == _DIM else 4
+    ctx = _CONTEXTS.get((device, dim))
     if ctx is None or ctx.max_planes < max_planes or ctx.max_lambda < max_lambda:
         if ctx is not None:
             max_planes = max(max_planes, ctx.max_planes)
             max_lambda = max(max_lambda, ctx.max_lambda)
             ctx.close()
-        ctx = _lib.Context(device=device, dim=_DIM, max_planes=max_planes, max_lambda=max_lambda)
+        ctx = _lib.Context(device=device, dim=dim, max_planes=max_planes, max_lambda=max_lambda)
         f, f_x, f_y = ao_frequency_tables()
         ctx.set_geometry(f, f_x, f_y)
-        _CONTEXTS[device] = ctx
+        _CONTEXTS[(device, dim)] = ctx
     return ctx
 
 
@@ -252,13 +262,12 @@ def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., plot=False, npsflin=1, dim=1280
                   three_lgs_mode=False, verbose=True):
     """Residual-phase PSD per field direction, [npsflin**2, dim, dim] in nm^2
     (psfrec.py:36-151), synthesised on the GPU."""
-    if dim != _DIM:
-        raise NotImplementedError('this build supports dim=%d only' % _DIM)
+    dim = _check_dim(dim)
     if three_lgs_mode and verbose:
         logger.info('Using three lasers mode')
     rec = draw_record(Cn2, h, seeing, L0, zenith)
     dirs = direction_perf(npsflin)
-    ctx = get_context(max_planes=max(16, dirs.shape[1]))
+    ctx = get_context(max_planes=max(16 if dim == _DIM else 4, dirs.shape[1]), dim=dim)
     out = np.empty((dirs.shape[1], dim, dim))
     ctx.psd(rec[None], dirs, _lgs_positions(three_lgs_mode), out=out)
     return out
@@ -274,8 +283,8 @@ def psd_to_psf(psd, pup, D, lbda, phase_static=None, samp=None, FoV=None, return
     samp = 2, FoV equal to the numerical field, no static phase."""
     psd = np.ascontiguousarray(psd, dtype=np.float64)
     dim = psd.shape[0]
-    if psd.ndim != 2 or dim != _DIM or psd.shape[1] != dim:
-        raise NotImplementedError('psd must be a %dx%d array' % (_DIM, _DIM))
+    if psd.ndim != 2 or dim not in _DIMS or psd.shape[1] != dim:
+        raise NotImplementedError('psd must be a square array of size %s' % (_DIMS,))
     if phase_static is not None or return_all:
         raise NotImplementedError('static phase / return_all are not on the hot path')
     if samp is not None and samp != 2:
@@ -287,7 +296,7 @@ def psd_to_psf(psd, pup, D, lbda, phase_static=None, samp=None, FoV=None, return
     FoVnum = (lbda / (2 * D)) * dim / (4.85 * 1.e-6)
     if FoV is not None and not np.allclose(FoV, FoVnum):
         raise NotImplementedError("FIXME: use gridddata or spline ?")
-    ctx = get_context()
+    ctx = get_context(dim=dim)
     ctx.load_psd(psd, 1)
     ctx.structure_function(1)
     out = np.empty((dim, dim))
@@ -301,10 +310,11 @@ def psf_muse(psd, lambdamuse):
     lam = np.atleast_1d(np.asarray(lambdamuse, dtype=float))
     if psd.ndim == 2:
         psd = psd[None]
-    if psd.ndim != 3 or psd.shape[1:] != (_DIM, _DIM):
-        raise NotImplementedError('psd must be [ndir, %d, %d]' % (_DIM, _DIM))
+    dim = psd.shape[1] if psd.ndim == 3 else 0
+    if psd.ndim != 3 or dim not in _DIMS or psd.shape[2] != dim:
+        raise NotImplementedError('psd must be [ndir, dim, dim] with dim in %s' % (_DIMS,))
     ndir = psd.shape[0]
-    ctx = get_context(max_planes=max(16, ndir), max_lambda=max(35, lam.size))
+    ctx = get_context(max_planes=max(16 if dim == _DIM else 4, ndir), max_lambda=max(35, lam.size), dim=dim)
     ctx.load_psd(psd, ndir)
     ctx.structure_function(ndir)
     out = np.empty((lam.size, _lib.PSF_DIM, _lib.PSF_DIM))
@@ -353,15 +363,17 @@ def fit_psf_cube(lbda, psfcube):
     return _table_from_fit(lam, fit)
 
 
-def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, verbose=True):
-    """Reconstruct a PSF from seeing, GL and L0 (psfrec.py:933-978): returns (table, psf)."""
+def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, verbose=True,
+                dim=_DIM):
+    """Reconstruct a PSF from seeing, GL and L0 (psfrec.py:933-978): returns (table, psf).
+    ``dim`` (1280, the reference's hard-coded grid, or 2560) is an extension of this backend."""
     if verbose:
         logger.info('Compute PSF with seeing=%.2f GL=%.2f L0=%.2f', seeing, GL, L0)
         if three_lgs_mode:
             logger.info('Using three lasers mode')
     lam = np.atleast_1d(np.asarray(lbda, dtype=float))
     fit, cube = compute_psf_batch(lam, [seeing], [GL], [L0], npsflin=npsflin, h=h,
-                                  three_lgs_mode=three_lgs_mode)
+                                  three_lgs_mode=three_lgs_mode, dim=dim)
     res = _table_from_fit(lam, fit[0])
     res.meta.update({'SEEING': seeing, 'GL': GL, 'L0': L0})
     res['SEEING'] = seeing
@@ -374,7 +386,8 @@ reconstruct_psf = compute_psf   # pre-1.0 name used by BASELINE.json's north_sta
 
 
 def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False,
-                      out_cube=None, out_fit=None, want_cube=True, device=None, max_planes=64, stream=None):
+                      out_cube=None, out_fit=None, want_cube=True, device=None, max_planes=None, stream=None,
+                      dim=_DIM):
     """Batched ``compute_psf``: one fused device pipeline for many (seeing, GL, L0[, h]) draws.
 
     ``h`` is one (h0, h1) pair or an array [ndraw, 2].  Returns (fit [ndraw, nl, FIT_NPAR],
@@ -392,8 +405,11 @@ def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs
     else:
         recs = draw_records(seeing, GL, L0, h)
     dirs = direction_perf(npsflin)
+    dim = _check_dim(dim)
+    if max_planes is None:
+        max_planes = 64 if dim == _DIM else 16
     ctx = get_context(max_planes=max(dirs.shape[1], min(max_planes, nd * dirs.shape[1])),
-                      max_lambda=max(35, lam.size), device=device)
+                      max_lambda=max(35, lam.size), device=device, dim=dim)
     if out_fit is None:
         out_fit = np.empty((nd, lam.size, _lib.FIT_NPAR))
     if out_cube is None and want_cube:

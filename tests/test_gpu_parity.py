@@ -37,14 +37,14 @@ def rel_to_peak(got, ref):
     return np.abs(np.asarray(got) - np.asarray(ref)).max() / np.abs(ref).max()
 
 
-def assert_image_close(got, ref, rtol=PSF_RTOL):
-    """Relative 1e-9: every pixel above 1e-6 of the peak agrees to rtol pointwise, and the
-    whole image agrees to rtol of the peak."""
+def assert_image_close(got, ref, rtol=PSF_RTOL, floor=1e-6):
+    """Relative 1e-9: every pixel above `floor` (1e-6) of the peak agrees to rtol pointwise, and
+    the whole image agrees to rtol of the peak."""
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape
     assert np.isfinite(got).all()
     assert rel_to_peak(got, ref) < rtol
-    sig = np.abs(ref) > 1e-6 * np.abs(ref).max()
+    sig = np.abs(ref) > floor * np.abs(ref).max()
     assert_allclose(got[sig], ref[sig], rtol=rtol, atol=0)
 
 
@@ -86,6 +86,80 @@ def test_psd_golden_config3(psfrec, golden):
 def test_three_layers_rejected(psfrec):
     with pytest.raises(ValueError):
         psfrec.simul_psd_wfm([0.5, 0.3, 0.2], (100, 5000, 10000), 1.0, 25.)
+
+
+# ---------------------------------------------------------------- BASELINE config 5: dim = 2560
+@pytest.fixture(scope='module')
+def psd5(psfrec):
+    return psfrec.simul_psd_wfm([0.7, 0.3], (100, 10000), 1.0, 25., dim=2560, verbose=False)
+
+
+def test_config5_psd_golden(psd5, golden):
+    """simul_psd_wfm(dim=2560) against the reference's own output (reduced fixture)."""
+    g = golden('ref_config5')
+    a, n, c = psd5[0], 2560, 1280
+    assert psd5.shape == (1, n, n)
+    assert_allclose(a[c - 48:c + 48, c - 48:c + 48], g['psd_centre'], rtol=1e-10)
+    assert_allclose(a[::16, ::16], g['psd_lattice'], rtol=1e-10)
+    assert_allclose(a[[0, 1, c - 1, c, c + 1, n - 1]], g['psd_rows'], rtol=1e-10)
+    assert_allclose(a.sum(), g['psd_sum'], rtol=1e-12)
+    assert_allclose(a.max(), g['psd_max'], rtol=1e-12)
+
+
+def test_config5_telescope_otf(psfrec):
+    t = psfrec.get_context(dim=2560).get_otf()
+    ref = orc.telescope_otf(orc.pupil_mask(640, 1280, 0.14), 2560)
+    assert t.shape == (1282, 2560)
+    assert rel_to_peak(t[:1281], ref[:1281]) < 1e-13
+    assert np.all(t[1281] == 0)
+    assert_allclose(t[1280, 1280] * 2560 ** 2, 1.0, rtol=1e-15)
+
+
+def test_config5_psf_muse_golden(psfrec, psd5, golden):
+    """psf_muse on the 2560 grid (two 1280-point warp transforms + radix-2 combine per line)
+    against the reference's own output at the two ends of the 100-wavelength range."""
+    g = golden('ref_config5')
+    got = psfrec.psf_muse(psd5[0], g['lbda'])
+    assert got.shape == g['psf_muse'].shape
+    for k in range(got.shape[0]):
+        assert_image_close(got[k], g['psf_muse'][k])
+
+
+def test_config5_psd_to_psf_full_grid(psfrec, psd5):
+    pup = orc.pupil_mask(640, 1280, 0.14)
+    got = psfrec.psd_to_psf(psd5[0], pup, 8, 700e-9, samp=2)
+    ref = orc.psd_to_psf(psd5[0], pup, 8, 700e-9)
+    # two FP64 2560^2 transforms (pocketfft vs. ours) differ by ~4e-19 absolute = 1e-15 of the peak,
+    # which is 1.2e-9 of the faintest pixels above 1e-6 of the peak: pointwise bar from 1e-5 up here
+    assert rel_to_peak(got, ref) < 1e-13
+    assert_image_close(got, ref, floor=1e-5)
+    assert_allclose(got.sum(), 1.0, rtol=1e-12)
+
+
+def test_config5_hundred_wavelengths(psfrec, psd5):
+    """All 100 wavelengths of config 5 in one call; the pruned path equals the full-grid path
+    resampled by the oracle's psf_muse tail at a few of them."""
+    lam = np.linspace(490, 930, 100)
+    cube = psfrec.psf_muse(psd5[0], lam)
+    assert cube.shape == (100, 40, 40) and np.isfinite(cube).all()
+    assert_allclose(cube.sum(axis=(1, 2)), 1.0, rtol=1e-12)
+    ref = orc.psf_muse(psd5[0], lam[[0, 57]])
+    assert_image_close(cube[0], ref[0])
+    assert_image_close(cube[57], ref[1])
+
+
+def test_config5_compute_psf(psfrec):
+    """compute_psf(dim=2560): the fitted FWHM moves by < 1 % against the 1280 grid (the wider
+    fitting PSD only adds far wings) and matches the oracle run at dim=2560."""
+    lam = np.array([500., 700., 900.])
+    tab, cube = psfrec.compute_psf(lam, 1.0, 0.7, 25., verbose=False, dim=2560)
+    ref, ref_cube = orc.compute_psf(lam, 1.0, 0.7, 25., dim=2560)
+    for k in range(3):
+        assert_image_close(cube[k], ref_cube[k])
+    assert_allclose(tab['fwhm'][:, 0], ref['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(tab['n'], ref['n'], rtol=FIT_RTOL)
+    tab1, _ = psfrec.compute_psf(lam, 1.0, 0.7, 25., verbose=False)
+    assert_allclose(tab['fwhm'][:, 0], tab1['fwhm'][:, 0], rtol=1e-2)
 
 
 # ---------------------------------------------------------------- structure function / psd_to_psf (a8)
