@@ -492,20 +492,25 @@ int psfr_mean_refit(psfr_ctx* c, int ncube, int nlam, const double* cubes, doubl
     PSFR_CUDA(c, cudaSetDevice(c->device));
     const size_t elems = (size_t)nlam * kPSF * kPSF;
     const size_t cap = (size_t)c->max_planes * c->max_lambda * kPSF * kPSF;
-    const double* src = cubes;
     double* mean = c->d_cube2;
-    if (!is_device_ptr(cubes)) {
-        if ((size_t)ncube * elems > cap) {
-            // too many cubes for the staging buffer: accumulate on the host side of the ABI is not
-            // allowed (no CPU path) -> stream them through in slabs and sum on the device
-            return set_error(c, PSFR_E_CAPACITY, "ncube=%d host cubes exceed the staging capacity; pass a device pointer", ncube);
-        }
-        int rc = to_device(c, c->d_cube, cubes, (size_t)ncube * elems * sizeof(double), s);
+    int rc = PSFR_OK;
+    if (is_device_ptr(cubes)) {
+        rc = run_mean(c, ncube, (int)elems, cubes, mean, s, true, true, ncube);
         if (rc) return rc;
-        src = c->d_cube;
+    } else {
+        // host cubes stream through the staging buffer in slabs; the running sum keeps the
+        // input order, so the result does not depend on the slab size
+        const int slab = (int)std::max<size_t>(1, cap / elems);
+        if (elems > cap) return set_error(c, PSFR_E_CAPACITY, "nlam=%d exceeds the staging capacity", nlam);
+        for (int k0 = 0; k0 < ncube; k0 += slab) {
+            const int n = std::min(slab, ncube - k0);
+            rc = to_device(c, c->d_cube, cubes + (size_t)k0 * elems, (size_t)n * elems * sizeof(double), s);
+            if (rc) return rc;
+            rc = run_mean(c, n, (int)elems, c->d_cube, mean, s, k0 == 0, k0 + n == ncube, ncube);
+            if (rc) return rc;
+            if (k0 + n < ncube) PSFR_CUDA(c, cudaStreamSynchronize(s));   // pageable source may be reused
+        }
     }
-    int rc = run_mean(c, ncube, (int)elems, src, mean, s);
-    if (rc) return rc;
     if (out_fit) {
         double* fit = is_device_ptr(out_fit) ? out_fit : c->d_fit;
         rc = run_fit(c, nlam, kPSF, kPSF, mean, fit, s);

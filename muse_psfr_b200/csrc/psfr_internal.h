@@ -136,8 +136,9 @@ int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s);
 // two Moffat convolutions; img index = draw*nlam + lam
 int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s);
 int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s);
+// out = (running sum of the cubes) ; first: start from zero, last: divide by ntotal
 int run_mean(Ctx* c, int ncube, int plane_elems, const double* cubes_dev, double* out_dev,
-             cudaStream_t s);
+             cudaStream_t s, bool first, bool last, int ntotal);
 int run_polyfit(Ctx* c, int nseries, int nlam, int deg, const double* lb_dev, const double* y_dev,
                 double* coef_dev, cudaStream_t s);
 

@@ -412,14 +412,14 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
 
 // ---------------------------------------------------------------- mean of cubes
 __global__ void mean_kernel(const double* __restrict__ cubes, int ncube, size_t elems,
-                            double* __restrict__ out) {
+                            double* __restrict__ out, int first, int last, int ntotal) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= elems) return;
-    // pairwise-free straight sum in input order, then /ncube (np.mean uses pairwise blocks of
-    // 8 along the reduced axis only for contiguous reductions; axis 0 reduces plane by plane)
-    double t = 0.0;
+    // straight sum in input order (np.mean over axis 0 reduces plane by plane), then / ntotal;
+    // `first` / `last` let the caller stream the cubes through in slabs with identical rounding
+    double t = first ? 0.0 : out[i];
     for (int k = 0; k < ncube; ++k) t += cubes[(size_t)k * elems + i];
-    out[i] = t / ncube;
+    out[i] = last ? t / ntotal : t;
 }
 
 // ---------------------------------------------------------------- polynomial smoothing
@@ -548,8 +548,10 @@ int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit
     return PSFR_OK;
 }
 
-int run_mean(Ctx* c, int ncube, int plane_elems, const double* cubes_dev, double* out_dev, cudaStream_t s) {
-    mean_kernel<<<(plane_elems + 255) / 256, 256, 0, s>>>(cubes_dev, ncube, (size_t)plane_elems, out_dev);
+int run_mean(Ctx* c, int ncube, int plane_elems, const double* cubes_dev, double* out_dev, cudaStream_t s,
+             bool first, bool last, int ntotal) {
+    mean_kernel<<<(plane_elems + 255) / 256, 256, 0, s>>>(cubes_dev, ncube, (size_t)plane_elems, out_dev,
+                                                          first ? 1 : 0, last ? 1 : 0, ntotal);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }

@@ -12,8 +12,13 @@ from math import gamma
 
 import numpy as np
 
-from . import _lib
+from . import _fits, _lib
 from ._lib import PsfrError
+
+__all__ = ['compute_psf_from_sparta', 'compute_psf', 'compute_psf_batch', 'reconstruct_psf', 'create_sparta_table',
+           'fit_psf_with_polynom', 'simul_psd_wfm', 'psd_to_psf', 'psf_muse', 'convolve_final_psf', 'fit_psf_cube',
+           'muse_intrinsic_psf', 'direction_perf', 'seeing2r01', 'pupil_mask', 'select_sparta_rows', 'FitTable',
+           'PsfrError', 'MIN_L0', 'MAX_L0']
 
 logger = logging.getLogger('muse_psfr.psfrec')   # the reference's logger name (tests assert on it)
 
@@ -447,3 +452,131 @@ def fit_psf_with_polynom(lbda, fwhm, beta, deg=(5, 5), output=0):
         res['fwhm_fit'] = np.polyval(fwhm_pol, lbf)
         res['beta_fit'] = np.polyval(beta_pol, lbf)
     return res
+
+
+# --------------------------------------------------------------------------- SPARTA shell
+def select_sparta_rows(values, mean_of_lgs=True, verbose=False):
+    """Row rejection and laser averaging of ``compute_psf_from_sparta`` (psfrec.py:1041-1076).
+
+    ``values``: [nrows, 4, 3] = (SEEING, TUR_GND, L0) of the 4 lasers.  Returns a list of
+    (seeing, GL, L0, three_lgs_mode, row_idx, lgs_idx) and logs the reference's messages."""
+    values = np.asarray(values, dtype=float)
+    nrows = len(values)
+    jobs = []
+    for irow, v in enumerate(values, start=1):
+        # GL > 0 and MIN_L0 < L0 < MAX_L0: "apparently the 4th value is often crap" (psfrec.py:1047-1051)
+        ok = (v[:, 1] > 0) & (v[:, 2] < MAX_L0) & (v[:, 2] > MIN_L0)
+        nb_gs = int(ok.sum())
+        three_lgs_mode = nb_gs < 4
+        if nb_gs == 0:
+            if verbose:
+                logger.info('%d/%d : No valid values, skipping this row', irow, nrows)
+                logger.debug('Values: %s', v.tolist())
+            continue
+        elif nb_gs < 4:
+            if verbose:
+                logger.info('%d/%d : Using only %d values out of 4 after outliers '
+                            'rejection', irow, nrows, nb_gs)
+        if mean_of_lgs:
+            seeing, GL, L0 = v[ok].mean(axis=0)
+            jobs.append((seeing, GL, L0, three_lgs_mode, irow, -1))
+        else:
+            for i in np.where(ok)[0]:
+                jobs.append((v[i, 0], v[i, 1], v[i, 2], three_lgs_mode, irow, i + 1))
+    return jobs
+
+
+def _fit_columns(lam, fit):
+    """Columns of the reference's fit table for fit records [n, nl, FIT_NPAR] (flattened)."""
+    nl = lam.size
+    fit = np.asarray(fit).reshape(-1, _lib.FIT_NPAR)
+    tab = _table_from_fit(np.tile(lam, len(fit) // nl), fit)
+    return {k: tab[k] for k in tab.colnames}
+
+
+def compute_psf_from_sparta(filename, extname='SPARTA_ATM_DATA', npsflin=1, lmin=490, lmax=930, nl=35,
+                            lbda=None, h=(100, 10000), n_jobs=-1, plot=False, mean_of_lgs=True,
+                            verbose=True, device=None):
+    """Reconstruct a PSF from SPARTA data (psfrec.py:981-1120).
+
+    ``filename``: path of a FITS file, a binary file object, or an HDUList (this package's or
+    astropy's) holding the SPARTA table.  Every valid row (or laser) becomes one draw of a single
+    batched GPU call (the reference fans them out over joblib processes, psfrec.py:1082-1083;
+    ``n_jobs`` is accepted and only reported).  Returns an HDUList [PRIMARY, <extname>, FIT_ROWS,
+    FIT_MEAN, PSF_MEAN] - an ``astropy.io.fits.HDUList`` when astropy is installed, otherwise
+    the equivalent object of ``muse_psfr_b200._fits`` - or None when no row is valid."""
+    if plot:
+        raise NotImplementedError('plotting is outside the B200 hot path')
+    hdul = _fits.from_any(filename, only={extname.upper()})
+    sparta = hdul[extname]
+    tbl = sparta.data
+    out = _fits.HDUList([_fits.PrimaryHDU(), sparta.copy()])
+    nrows = len(tbl)
+    if nrows == 1:
+        n_jobs = 1
+    if lbda is None:
+        lbda = np.linspace(lmin, lmax, nl)
+    lbda = np.atleast_1d(np.asarray(lbda, dtype=float))
+    if verbose:
+        logger.info('Processing SPARTA table with %d values, njobs=%d ...', nrows, n_jobs)
+    values = np.array([[[row['LGS%d_%s' % (k, col)] for col in ('SEEING', 'TUR_GND', 'L0')]
+                        for k in range(1, 5)] for row in tbl], dtype=float).reshape(nrows, 4, 3)
+    jobs = select_sparta_rows(values, mean_of_lgs=mean_of_lgs, verbose=verbose)
+    if len(jobs) == 0:
+        logger.warning('No valid values')
+        return None
+
+    seeing, GL, L0, three, row_idx, lgs_idx = (np.array(c) for c in zip(*jobs))
+    if verbose:
+        for j in range(len(jobs)):      # the messages compute_psf / simul_psd_wfm log per draw
+            logger.info('Compute PSF with seeing=%.2f GL=%.2f L0=%.2f', seeing[j], GL[j], L0[j])
+            if three[j]:
+                logger.info('Using three lasers mode')
+    nj = len(jobs)
+    fit = np.empty((nj, lbda.size, _lib.FIT_NPAR))
+    cube = np.empty((nj, lbda.size, _lib.PSF_DIM, _lib.PSF_DIM))
+    for mode in (False, True):          # the LGS geometry is a per-call constant: 4-LGS and 3-LGS batches
+        sel = np.where(three == mode)[0]
+        if sel.size:
+            f, c = compute_psf_batch(lbda, seeing[sel], GL[sel], L0[sel], npsflin=npsflin, h=h,
+                                     three_lgs_mode=bool(mode), device=device)
+            fit[sel], cube[sel] = f, c
+
+    # fit values of all rows in one table (psfrec.py:1086-1101)
+    cols = _fit_columns(lbda, fit)
+    rep = lbda.size
+    cols['SEEING'] = np.repeat(seeing, rep)
+    cols['GL'] = np.repeat(GL, rep)
+    cols['L0'] = np.repeat(L0, rep)
+    cols['row_idx'] = np.repeat(np.arange(1, nj + 1, dtype=np.int64), rep)
+    cols['lgs_idx'] = np.repeat(lgs_idx.astype(np.int64), rep)
+    out.append(_fits.table_to_hdu(cols, name='FIT_ROWS'))
+
+    # mean PSF over the draws, refit, median seeing / GL / L0 (psfrec.py:1104-1113)
+    ctx = get_context(max_lambda=max(35, lbda.size), device=device)
+    psftot = np.empty((lbda.size, _lib.PSF_DIM, _lib.PSF_DIM))
+    fit_mean = np.empty((lbda.size, _lib.FIT_NPAR))
+    ctx.mean_refit(nj, lbda.size, cube, psftot, fit_mean)
+    med = np.median(np.stack([seeing, GL, L0], axis=1), axis=0)
+    meta = {'SEEING': float(med[0]), 'GL': float(med[1]), 'L0': float(med[2])}
+    out.append(_fits.table_to_hdu(_fit_columns(lbda, fit_mean[None]), meta=meta, name='FIT_MEAN'))
+    out.append(_fits.ImageHDU(data=psftot, name='PSF_MEAN'))
+    try:
+        return _fits.to_astropy(out)
+    except ImportError:
+        return out
+
+
+def create_sparta_table(nlines=1, seeing=1, L0=25, GL=0.7, bad_l0=False, outfile=None):
+    """Helper function to create a SPARTA table with the given seeing, L0, and GL values
+    (psfrec.py:1123-1141).  Returns the table HDU; ``outfile`` may be a path or a file object."""
+    cols = {}
+    for k in range(1, 5):
+        for col, v in (('SEEING', seeing), ('TUR_GND', GL), ('L0', L0)):
+            cols['LGS%d_%s' % (k, col)] = np.full(nlines, float(v))
+    if bad_l0:
+        cols['LGS4_L0'] = np.full(nlines, 150.0)
+    hdu = _fits.table_to_hdu(cols, name='SPARTA_ATM_DATA')
+    if outfile is not None:
+        hdu.writeto(outfile, overwrite=True)
+    return hdu
