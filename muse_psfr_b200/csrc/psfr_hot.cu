@@ -169,7 +169,8 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     }
                     continue;
                 }
-                const double negc = -cl, ncut = -p.cut;
+                const double negc = -cl;
+                const unsigned cut_hi = (unsigned)__double2hiint(-p.cut);
                 // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
                 const uint16_t* kx = p.kidx + (size_t)lam * kNS;
                 int ka[3];
@@ -188,8 +189,10 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         const double xc = negc * sD[n1], xd = negc * sD[kN + n1];
                         // outside the pupil-autocorrelation support the OTF is exactly zero; below
                         // the underflow cut it is flushed to zero
-                        const bool dead = ((ta == 0.0) | (xa < ncut)) & ((tb == 0.0) | (xb_ < ncut)) &
-                                          ((tc == 0.0) | (xc < ncut)) & ((td == 0.0) | (xd < ncut));
+                        const bool dead = (is_zero_bits(ta) | below_cut(xa, cut_hi)) &
+                                          (is_zero_bits(tb) | below_cut(xb_, cut_hi)) &
+                                          (is_zero_bits(tc) | below_cut(xc, cut_hi)) &
+                                          (is_zero_bits(td) | below_cut(xd, cut_hi));
                         if (__all_sync(0xffffffffu, dead)) {
                             v[i] = make_double2(0.0, 0.0);
                             v[i + 1] = make_double2(0.0, 0.0);
@@ -271,63 +274,140 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
 }
 
 // ---------------- pruned column pass
-// line f = ((draw*nlam + lam)*40 + m): sampled rows 2m, 2m+1 of that PSF, summed over the
-// ndir planes of the draw, Hermitian-extended along the half-plane row index.
+// line f = ((draw*nlam + lam)*40 + m): sampled rows 2m, 2m+1 of that PSF (adjacent in Y, one
+// contiguous 2*Rows*16-byte block), summed over the ndir planes of the draw, Hermitian-extended
+// along the half-plane row index, transformed, and only the 80 sampled outputs kept:
+//   S[img][2m + c][j] = scale * (-1)^(k_{2m+c} + k_j) * {Re, Im}(X[k_j]).
+// Every warp owns a private tile that a TMA bulk copy fills while the warp transforms the
+// previous line (the tile is dead as soon as its values sit in registers), so the kernel
+// streams Y at HBM speed instead of waiting on 80 dependent 16-byte loads per lane.
 template <int NF>
-struct LoadSampledPair {
-    using D = Dim<NF>;
-    const double2* Y;  // [nplanes][nlam][kNS][Rows]
-    int nlam, ndir;
-    __device__ void operator()(int f, int lane, double2* v, int sub) const {
-        const int m = f % (kNS / 2), img = f / (kNS / 2);
-        const int lam = img % nlam, draw = img / nlam;
-#pragma unroll
-        for (int i = 0; i < 40; ++i) v[i] = make_double2(0.0, 0.0);
-        for (int d = 0; d < ndir; ++d) {
-            const double2* c1 = Y + (((size_t)(draw * ndir + d) * nlam + lam) * kNS + 2 * m) * D::Rows;
-            const double2* c2 = c1 + D::Rows;
-#pragma unroll
-            for (int i = 0; i < 40; ++i) {
-                const int n = slot_e<NF>(i, lane, sub);
-                if (n <= D::NH) {
-                    const double2 r1 = __ldg(c1 + n), r2 = __ldg(c2 + n);
-                    v[i].x += r1.x - r2.y;
-                    v[i].y += r1.y + r2.x;
-                } else {
-                    const double2 r1 = __ldg(c1 + (D::N - n)), r2 = __ldg(c2 + (D::N - n));
-                    v[i].x += r1.x + r2.y;
-                    v[i].y += r2.x - r1.y;
-                }
-            }
-        }
-    }
+struct ColCfg {
+    static constexpr int Warps = NF == 1 ? 6 : 4;
+    static constexpr int TileElems = 2 * Dim<NF>::Rows;                 // double2 per tile
+    static constexpr uint32_t TileBytes = TileElems * sizeof(double2);
+    static constexpr size_t Smem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
+                                   (size_t)Warps * (TileBytes + G::XBUF * sizeof(double));
+    static_assert(TileBytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+    static_assert(Smem <= 232448, "column kernel shared memory exceeds the 227 KB per-CTA limit");
 };
 
-// samples S[img][i][j] = scale * (-1)^(X_i + Y_j) * F[xi_i, eta_j]
-template <int NF>
-struct StoreSamples {
+struct ColParams {
+    const double2* Y;      // [nplanes][nlam][kNS][Rows]
     double* S;             // [nimg][kNS][kNS]
     const uint16_t* kidx;  // [nlam][kNS]
-    int nlam;
+    const double2* wsamp;  // [nlam][2][kNS] (NF = 2)
+    int nlines, nlam, ndir;
     double scale;
-    __device__ void operator()(int f, int lane, const double* xb) const {
+};
+
+template <int NF>
+__global__ void __launch_bounds__(ColCfg<NF>::Warps * 32, 1)
+hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
+    using D = Dim<NF>;
+    using C = ColCfg<NF>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);              // one mbarrier per warp
+    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
+    double2* tw2 = tw1 + G::TW1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* tile = tw2 + G::TW2 + (size_t)warp * C::TileElems;
+    double* xb = reinterpret_cast<double*>(tw2 + G::TW2 + (size_t)C::Warps * C::TileElems) + (size_t)warp * G::XBUF;
+    uint64_t* bar = bars + warp;
+
+    for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int gw = blockIdx.x * C::Warps + warp, nw = gridDim.x * C::Warps;
+    // tile of (line f, direction d)
+    auto src_of = [&](int f, int d) {
         const int m = f % (kNS / 2), img = f / (kNS / 2);
-        const int lam = img % nlam;
-        const uint16_t* kx = kidx + (size_t)lam * kNS;
+        const int lam = img % p.nlam, draw = img / p.nlam;
+        return p.Y + (((size_t)(draw * p.ndir + d) * p.nlam + lam) * kNS + 2 * m) * D::Rows;
+    };
+    auto fetch = [&](int f, int d) {
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, C::TileBytes);
+            tma_load_1d(tile, src_of(f, d), C::TileBytes, bar);
+        }
+    };
+    if (gw < p.nlines) fetch(gw, 0);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int f = gw; f < p.nlines; f += nw) {
+        const int m = f % (kNS / 2), img = f / (kNS / 2), lam = img % p.nlam;
+        const uint16_t* kx = p.kidx + (size_t)lam * kNS;
+        int kj[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) kj[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
+        double2 z[3];
+#pragma unroll 1
+        for (int sub = 0; sub < NF; ++sub) {
+            double2 v[40];
+#pragma unroll
+            for (int i = 0; i < 40; ++i) v[i] = make_double2(0.0, 0.0);
+#pragma unroll 1
+            for (int d = 0; d < p.ndir; ++d) {
+                // NF = 2 walks the tiles of the line twice (even, then odd elements)
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                const double2* c1 = tile;
+                const double2* c2 = tile + D::Rows;
+#pragma unroll
+                for (int i = 0; i < 40; ++i) {
+                    const int n = slot_e<NF>(i, lane, sub);
+                    if (n <= D::NH) {
+                        const double2 r1 = c1[n], r2 = c2[n];
+                        v[i].x += r1.x - r2.y;
+                        v[i].y += r1.y + r2.x;
+                    } else {
+                        const double2 r1 = c1[D::N - n], r2 = c2[D::N - n];
+                        v[i].x += r1.x + r2.y;
+                        v[i].y += r2.x - r1.y;
+                    }
+                }
+                __syncwarp();
+                // the tile is dead: prefetch the next one of this warp's sequence
+                if (d + 1 < p.ndir) fetch(f, d + 1);
+                else if (sub + 1 < NF) fetch(f, 0);
+                else if (f + nw < p.nlines) fetch(f + nw, 0);
+            }
+            warp_fft<kR3>(v, xb, tw1, tw2, lane);
+            double2 fz[3];
+#pragma unroll
+            for (int cpt = 0; cpt < 2; ++cpt) {
+                fft_dump<kR3>(v, xb, lane, cpt);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 3; ++i) comp_set(fz[i], cpt, xb[nat_addr(kj[i] % kNB)]);
+                __syncwarp();
+            }
+            if (NF == 1 || sub == 0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) z[i] = fz[i];
+            } else {
+                const double2* ws = p.wsamp + (size_t)lam * 2 * kNS;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (lane + 32 * i < kNS) z[i] = cadd(z[i], cmul(fz[i], __ldg(ws + lane + 32 * i)));
+            }
+        }
         const int k1 = __ldg(kx + 2 * m), k2 = __ldg(kx + 2 * m + 1);
-        double* o = S + ((size_t)img * kNS + 2 * m) * kNS;
+        double* o = p.S + ((size_t)img * kNS + 2 * m) * kNS;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int j = lane + 32 * i;
             if (j < kNS) {
-                const int kj = __ldg(kx + j);
-                const double2 z = nat_get<NF>(xb, kj);
-                o[j] = (((k1 + kj) & 1) ? -scale : scale) * z.x;
-                o[kNS + j] = (((k2 + kj) & 1) ? -scale : scale) * z.y;
+                o[j] = (((k1 + kj[i]) & 1) ? -p.scale : p.scale) * z[i].x;
+                o[kNS + j] = (((k2 + kj[i]) & 1) ? -p.scale : p.scale) * z[i].y;
             }
         }
     }
-};
+}
 
 template <int NF>
 static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
@@ -354,9 +434,18 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     c->hot_psfs += (long long)nplanes * nlam;
     // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
     // inverse transform); psf_muse averages the directions.
-    const double scale = 1.0 / ndir;
-    return launch_pass<NF>(c, LoadSampledPair<NF>{c->d_ybuf, nlam, ndir},
-                           StoreSamples<NF>{c->d_samp, c->d_kidx, nlam, scale}, ndraw * nlam * (kNS / 2), s);
+    static bool attr2_set = false;
+    if (!attr2_set) {
+        PSFR_CUDA(c, cudaFuncSetAttribute(hot_cols_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)ColCfg<NF>::Smem));
+        attr2_set = true;
+    }
+    ColParams q{c->d_ybuf, c->d_samp, c->d_kidx, c->d_wsamp, ndraw * nlam * (kNS / 2), nlam, ndir, 1.0 / ndir};
+    int cgrid = (q.nlines + ColCfg<NF>::Warps - 1) / ColCfg<NF>::Warps;
+    if (cgrid > c->sm_count) cgrid = c->sm_count;
+    hot_cols_kernel<NF><<<cgrid, ColCfg<NF>::Warps * 32, ColCfg<NF>::Smem, s>>>(q, c->d_tw);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
 }
 
 int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
