@@ -10,9 +10,16 @@
 //   n = n1*(N/8) + n2*R3 + n3,   k = k1 + 8*k2 + 64*k3
 //   load   : v[j*8+n1]   = x[n1*(N/8) + t + 32*j]                 (j<5, lane t)
 //   pass 1 : radix-8 over n1, times w_N^{(t+32j) k1}
-//   xchg 1 : lane t takes pairs p = t+32*j' -> (k1,n3) = (p/R3, p%R3), all n2
+//   xchg 1 : lane t takes pairs p = t+32*j' -> (k1,n3) = (p%8, p/8), all n2
 //   pass 2 : radix-8 over n2, times w_{N/8}^{n3 k2}
 //   xchg 2 : lane t takes q = t+32*u -> (k1,k2) = (q%8, q/8), all n3
+// Shared-memory layouts (8-byte words, 16 bank pairs; a 64-bit warp access is two half-warp
+// wavefronts when the 16 lanes of each half hit 16 distinct bank pairs):
+//   xchg 1 : word k1*S1 + n2*R3 + n3 with S1 = N/8 + 2 = 2 (mod 16): stores are lane-
+//            contiguous, loads see k1 = all eight values and two adjacent n3 per half-warp
+//            -> 2 k1 + n3 distinct
+//   xchg 2 : word 64*n3 + (q xor 8*(n3 & 1)), q = k1 + 8 k2: compact, and both the stores
+//            (k1 x two adjacent n3) and the loads (k1 x two adjacent k2) are conflict-free
 //   pass 3 : radix-R3 over n3 (Good-Thomas 5 x R3/5, no inner twiddles)
 //   result : v[u*R3+k3]  = X[t + 32*u + 64*k3]
 //
@@ -132,11 +139,9 @@ struct FftGeom {
     static constexpr int N = 64 * R3;
     static constexpr int TL = 32;            // lanes per transform
     static constexpr int NQ = 64 / TL;       // (k1,k2) pairs per lane in pass 3
-    static constexpr int S1 = N / 8 + 4;     // exchange-1 row stride (doubles)
-    static constexpr int S2 = R3 + 1;        // exchange-2 row stride (doubles)
+    static constexpr int S1 = N / 8 + 2;     // exchange-1 row stride (doubles)
     static constexpr int NAT = N + N / 16;   // skewed natural-order dump
-    static constexpr int XBUF = (8 * S1 > 64 * S2 ? (8 * S1 > NAT ? 8 * S1 : NAT)
-                                                  : (64 * S2 > NAT ? 64 * S2 : NAT));
+    static constexpr int XBUF = (8 * S1 > NAT ? 8 * S1 : NAT);   // exchange 2 is compact (N words)
     static constexpr int TW1 = 5 * 7 * TL;   // double2 entries: [j][k1-1][t]
     static constexpr int TW2 = 7 * R3;       // double2 entries: [k2-1][n3]
     static_assert(N == 40 * TL, "only the one-warp-per-transform geometry is implemented");
@@ -174,7 +179,7 @@ PSFR_HD void fft_x1_load(double2* v, const double* sm, int t, int c) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int p = t + G::TL * j;
-        const int base = (p / R3) * G::S1 + (p % R3);
+        const int base = (p % 8) * G::S1 + (p / 8);
 #pragma unroll
         for (int n2 = 0; n2 < 8; ++n2) comp_set(v[j * 8 + n2], c, sm[base + n2 * R3]);
     }
@@ -185,7 +190,7 @@ PSFR_HD void fft_pass2(double2* v, const double2* tw2, int t) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        const int n3 = (t + G::TL * j) % R3;
+        const int n3 = (t + G::TL * j) / 8;
         dft8(v + j * 8);
 #pragma unroll
         for (int k2 = 1; k2 < 8; ++k2)
@@ -199,9 +204,10 @@ PSFR_HD void fft_x2_store(const double2* v, double* sm, int t, int c) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int p = t + G::TL * j;
-        const int base = (p / R3) * G::S2 + (p % R3);
+        const int n3 = p / 8;
+        const int base = 64 * n3 + ((p % 8) ^ (8 * (n3 & 1)));
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) sm[base + 8 * k2 * G::S2] = comp_get(v[j * 8 + k2], c);
+        for (int k2 = 0; k2 < 8; ++k2) sm[base ^ (8 * k2)] = comp_get(v[j * 8 + k2], c);   // q = k1 + 8 k2
     }
 }
 
@@ -212,7 +218,7 @@ PSFR_HD void fft_x2_load(double2* v, const double* sm, int t, int c) {
     for (int u = 0; u < G::NQ; ++u)
 #pragma unroll
         for (int n3 = 0; n3 < R3; ++n3)
-            comp_set(v[u * R3 + n3], c, sm[(t + G::TL * u) * G::S2 + n3]);
+            comp_set(v[u * R3 + n3], c, sm[64 * n3 + ((t + G::TL * u) ^ (8 * (n3 & 1)))]);
 }
 
 template <int R3>
