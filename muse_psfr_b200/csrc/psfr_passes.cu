@@ -182,6 +182,68 @@ struct StoreAbs2 {
     }
 };
 
+// Structure function rows: D[a][b] = centre - value (psfrec.py:721: 2 (bg[0,0] - bg), centred),
+// written straight from the column transform, with the smallest D of each row recorded for the
+// underflow cut of stage B and the pad row zeroed.  centre[plane] comes from StoreCentre below,
+// which runs the very same transform on the line that holds the DC term.
+template <int NF>
+struct StoreDphi {
+    using D = Dim<NF>;
+    double* out;            // [nplanes][Rows][N]
+    const double* centre;   // [nplanes]
+    double* dmin;           // [nplanes][Rows]
+    double scale;
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        const int plane = f / D::Pairs, m = f % D::Pairs;
+        const int o1 = 2 * m, o2 = o1 + 1;
+        double* r1 = out + ((size_t)plane * D::Rows + o1) * D::N;
+        const bool ok2 = o2 <= D::NH;
+        const double c0 = __ldg(centre + plane);
+        double m1 = 1e300, m2 = ok2 ? 1e300 : 0.0;
+#pragma unroll 4
+        for (int i = 0; i < 40 * NF; ++i) {
+            const int b = lane + 32 * i;
+            const double2 z = nat_get<NF>(xb, (b + D::NH) % D::N);
+            const double s1 = ((o1 + b) & 1) ? -scale : scale;
+            const double d1 = c0 - s1 * z.x;
+            const double d2 = ok2 ? c0 + s1 * z.y : 0.0;
+            r1[b] = d1;
+            r1[D::N + b] = d2;
+            m1 = fmin(m1, d1);
+            m2 = fmin(m2, d2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        }
+        if (lane == 0) {
+            dmin[(size_t)plane * D::Rows + o1] = m1;
+            dmin[(size_t)plane * D::Rows + o2] = m2;
+        }
+    }
+};
+
+// line f = plane: the pair that holds row N/2; keeps only centre[plane] = scale * Re X[0]
+template <int NF>
+struct StoreCentre {
+    using D = Dim<NF>;
+    double* centre;
+    double scale;
+    __device__ void operator()(int f, int lane, const double* xb) const {
+        // row N/2 is even (o1 of its pair), column b = N/2 reads output (b + N/2) % N = 0; sign (+)
+        if (lane == 0) centre[f] = scale * nat_get<NF>(xb, 0).x;
+    }
+};
+
+// loader wrapper: line f of the wrapped loader is line f * stride + offset
+template <class L>
+struct LoadStrided {
+    L inner;
+    int stride, offset;
+    __device__ void operator()(int f, int lane, double2* v, int sub) const { inner(f * stride + offset, lane, v, sub); }
+};
+
 // ------------------------------------------------------------------ small elementwise kernels
 __global__ void pupil_kernel(double* pup, int nh, double radius, double oc) {
     // pupil_mask(N/4, N/2, oc) (psfrec.py:190-203): rho = hypot(x-c, y-c)/radius
@@ -201,46 +263,6 @@ __global__ void finalize_otf_kernel(double* t, size_t live, size_t total, double
 }
 
 // ------------------------------------------------------------------ drivers
-__global__ void stash_centre_kernel(const double* d, double* centre, int nplanes, size_t per, size_t at) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < nplanes) centre[p] = d[(size_t)p * per + at];
-}
-
-// D[a][b] = Draw[N/2][N/2] - Draw[a][b], pad row zero (psfrec.py:721: 2*(bg[0,0] - bg)); one
-// block per row, which also records the smallest D of the row for the underflow cut of stage B
-__global__ void __launch_bounds__(256)
-finalize_dphi_kernel(double* d, const double* centre, double* dmin, int n, int rows) {
-    __shared__ double red[8];
-    const int row = blockIdx.x % rows, plane = blockIdx.x / rows;
-    double* r = d + ((size_t)plane * rows + row) * n;
-    const double c0 = centre[plane];
-    double m = 1e300;
-    for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        const double v = (row > n / 2) ? 0.0 : c0 - r[b];
-        r[b] = v;
-        m = fmin(m, v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fmin(m, red[w]);
-        dmin[(size_t)plane * rows + row] = m;
-    }
-}
-
-static int launch_finalize_dphi(Ctx* c, int nplanes, cudaStream_t s) {
-    double* centre = c->d_misc + kMiscCentre;  // scratch area reserved for plane centres
-    stash_centre_kernel<<<(nplanes + 127) / 128, 128, 0, s>>>(c->d_dphi, centre, nplanes, (size_t)c->rows * c->N,
-                                                              (size_t)c->NH * c->N + c->NH);
-    PSFR_LAUNCH_CHECK(c);
-    finalize_dphi_kernel<<<nplanes * c->rows, 256, 0, s>>>(c->d_dphi, centre, c->d_dmin, c->N, c->rows);
-    PSFR_LAUNCH_CHECK(c);
-    c->planes_struct = nplanes;
-    return PSFR_OK;
-}
-
 template <int NF>
 static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s) {
     using D = Dim<NF>;
@@ -250,10 +272,18 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s) {
     if (rc) return rc;
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
     const double L = 16.0;
-    rc = launch_pass<NF>(c, LoadHermitianPair<NF>{c->d_bt, D::Pairs, D::NH},
-                         StoreRealRows<NF>{c->d_dphi, D::Pairs, D::Rows, D::NH, 2.0 / (L * L), 1}, nplanes * D::Pairs, s);
+    const double scale = 2.0 / (L * L);
+    double* centre = c->d_misc + kMiscCentre;  // scratch area reserved for plane centres
+    const LoadHermitianPair<NF> cols{c->d_bt, D::Pairs, D::NH};
+    // the DC term first (one line per plane: the pair of row N/2), then every line with the
+    // subtraction fused into the store - bit-identical to subtracting after the fact
+    rc = launch_pass<NF>(c, LoadStrided<LoadHermitianPair<NF>>{cols, D::Pairs, D::NH / 2},
+                         StoreCentre<NF>{centre, scale}, nplanes, s);
     if (rc) return rc;
-    return launch_finalize_dphi(c, nplanes, s);
+    rc = launch_pass<NF>(c, cols, StoreDphi<NF>{c->d_dphi, centre, c->d_dmin, scale}, nplanes * D::Pairs, s);
+    if (rc) return rc;
+    c->planes_struct = nplanes;
+    return PSFR_OK;
 }
 
 int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
