@@ -172,7 +172,43 @@ __device__ __forceinline__ void warp_sum_vec(double* v) {
     }
 }
 
-// accumulate normal equations at x over this lane's pixels, then reduce over the warp
+// 1/u for u in [1, 1e300): hardware seed + two Newton steps (no special cases to test for)
+__device__ __forceinline__ double rcp_pos(double u) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(u));
+    double e = fma(-u, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-u, r, 1.0);
+    return fma(r, e, r);
+}
+
+// one pixel's contribution to the normal equations
+__device__ __forceinline__ void accumulate_pixel(double dp, double dq, double pix, double I, double n, double ia2,
+                                                 double ia, double* sums) {
+    const double rho2 = (dp * dp + dq * dq) * ia2;
+    const double uu = 1.0 + rho2;
+    const double lu = log(uu);
+    const double m = fast_exp(-n * lu);        // u^-n
+    const double f = I * m;
+    const double g = 2.0 * n * f * rcp_pos(uu);  // 2 I n u^(-n-1)
+    double J[kNP];
+    J[0] = m;
+    J[1] = g * dp * ia2;
+    J[2] = g * dq * ia2;
+    J[3] = g * rho2 * ia;
+    J[4] = -f * lu;
+    const double r = f - pix;
+#pragma unroll
+    for (int i = 0; i < kNP; ++i)
+#pragma unroll
+        for (int j = i; j < kNP; ++j) sums[pk(i, j)] = fma(J[i], J[j], sums[pk(i, j)]);
+#pragma unroll
+    for (int i = 0; i < kNP; ++i) sums[15 + i] = fma(J[i], r, sums[15 + i]);
+    sums[20] = fma(r, r, sums[20]);
+}
+
+// accumulate normal equations at x over this lane's pixels (two independent pixel chains per
+// trip so that the log / exp latencies overlap), then reduce over the warp
 __device__ __forceinline__ void accumulate(const double* __restrict__ img, int npx, int nx, const double* x,
                                            double* sums) {
 #pragma unroll
@@ -182,35 +218,24 @@ __device__ __forceinline__ void accumulate(const double* __restrict__ img, int n
     const int lane = threadIdx.x & 31;
     int pr = lane / nx, qc = lane % nx;          // once per call; then stepped incrementally
     const int dpr = 32 / nx, dqc = 32 % nx;
-    for (int idx = lane; idx < npx; idx += 32) {
-        const double dp = (double)pr - y0, dq = (double)qc - x0;
-        const double rho2 = (dp * dp + dq * dq) * ia2;
-        const double uu = 1.0 + rho2;
-        const double lu = log(uu);
-        const double m = fast_exp(-n * lu);        // u^-n
-        const double f = I * m;
-        const double g = 2.0 * n * f / uu;          // 2 I n u^(-n-1)
-        double J[kNP];
-        J[0] = m;
-        J[1] = g * dp * ia2;
-        J[2] = g * dq * ia2;
-        J[3] = g * rho2 * ia;
-        J[4] = -f * lu;
-        const double r = f - img[idx];
-#pragma unroll
-        for (int i = 0; i < kNP; ++i)
-#pragma unroll
-            for (int j = i; j < kNP; ++j) sums[pk(i, j)] = fma(J[i], J[j], sums[pk(i, j)]);
-#pragma unroll
-        for (int i = 0; i < kNP; ++i) sums[15 + i] = fma(J[i], r, sums[15 + i]);
-        sums[20] = fma(r, r, sums[20]);
+    auto step = [&]() {
         pr += dpr;
         qc += dqc;
         if (qc >= nx) {
             qc -= nx;
             ++pr;
         }
+    };
+    int idx = lane;
+    for (; idx + 32 < npx; idx += 64) {
+        const double dp0 = (double)pr - y0, dq0 = (double)qc - x0;
+        step();
+        const double dp1 = (double)pr - y0, dq1 = (double)qc - x0;
+        step();
+        accumulate_pixel(dp0, dq0, img[idx], I, n, ia2, ia, sums);
+        accumulate_pixel(dp1, dq1, img[idx + 32], I, n, ia2, ia, sums);
     }
+    if (idx < npx) accumulate_pixel((double)pr - y0, (double)qc - x0, img[idx], I, n, ia2, ia, sums);
     warp_sum_vec(sums);
 }
 
@@ -256,12 +281,20 @@ __device__ __forceinline__ void chol_solve(const double (&L)[kNP][kNP], double* 
 }
 
 __global__ void __launch_bounds__(kFitWarps * 32)
-fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __restrict__ out) {
+fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __restrict__ out,
+           int* __restrict__ next_image) {
     extern __shared__ double sm[];
     const int npx = ny * nx, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int image = blockIdx.x * kFitWarps + warp;
-    if (image >= nimg) return;                       // whole warp leaves; no block barrier is used below
     double* img = sm + (size_t)warp * (npx + nx);    // npx pixels + nx column weights
+    // images are handed to the warps by a global counter: the LM iteration count varies 3x
+    // between images, so a static one-image-per-warp grid ends in a long tail
+#pragma unroll 1
+    for (;;) {
+    int image = 0;
+    if (lane == 0) image = atomicAdd(next_image, 1);
+    image = __shfl_sync(0xffffffffu, image, 0);
+    if (image >= nimg) return;                       // whole warp leaves; no block barrier is used below
+    __syncwarp();
     double* colw = img + npx;
     const double* src = imgs + (size_t)image * npx;
     for (int i = lane; i < npx; i += 32) img[i] = src[i];
@@ -408,6 +441,8 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         o[PSFR_FIT_FLUX] = 3.141592653589793 * a * a * x[0] / (n - 1.0);
         o[15] = 0.0;
     }
+    __syncwarp();
+    }   // next image
 }
 
 // ---------------------------------------------------------------- mean of cubes
@@ -543,7 +578,11 @@ int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit
         PSFR_CUDA(c, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    fit_kernel<<<(nimg + kFitWarps - 1) / kFitWarps, kFitWarps * 32, smem, s>>>(img_dev, nimg, ny, nx, fit_dev);
+    int grid = (nimg + kFitWarps - 1) / kFitWarps;
+    const int resident = c->sm_count * 3;            // 166 registers x 128 threads: three CTAs per SM
+    if (grid > resident) grid = resident;
+    PSFR_CUDA(c, cudaMemsetAsync(c->d_counter + 1, 0, sizeof(int), s));
+    fit_kernel<<<grid, kFitWarps * 32, smem, s>>>(img_dev, nimg, ny, nx, fit_dev, c->d_counter + 1);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }
