@@ -165,7 +165,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_draws); cudaFree(c->d_misc); cudaFree(c->d_lam); cudaFree(c->d_kidx); cudaFree(c->d_frac);
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
-    cudaFree(c->d_twc); cudaFree(c->d_wsamp);
+    cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     HotTimer* t = timer_of(c);
     if (t) {
@@ -246,6 +246,8 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_frac, LM * kPSF));
     CK(dev_alloc(c, &c->d_kern_tt, P * kKW * kKW));
     CK(dev_alloc(c, &c->d_kern_mu, LM * kKW * kKW));
+    CK(dev_alloc(c, &c->d_khat_tt, P * 80 * 41));
+    CK(dev_alloc(c, &c->d_khat_mu, LM * 80 * 41));
     CK(dev_alloc(c, &c->d_cube, P * LM * kPSF * kPSF));
     CK(dev_alloc(c, &c->d_cube2, P * LM * kPSF * kPSF));
     CK(dev_alloc(c, &c->d_fit, P * LM * PSFR_FIT_NPAR));

@@ -75,6 +75,8 @@ struct Ctx {
     double* d_frac = nullptr;    // [max_lambda][kPSF] bilinear fractions
     double* d_kern_tt = nullptr; // [max_planes][41][41] normalised tip-tilt kernels
     double* d_kern_mu = nullptr; // [max_lambda][41][41] normalised MUSE kernels
+    double2* d_khat_tt = nullptr; // [max_planes][80][41] half spectra of the tip-tilt kernels
+    double2* d_khat_mu = nullptr; // [max_lambda][80][41] half spectra of the MUSE kernels
     double* d_cube = nullptr;    // [max_planes*max_lambda][40][40] staging for cubes
     double* d_cube2 = nullptr;   // second staging buffer
     double* d_fit = nullptr;     // [max_planes*max_lambda][PSFR_FIT_NPAR]
@@ -133,6 +135,9 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
                       cudaStream_t s);
 // samples -> 40x40 resampled + normalised cube (psf_muse tail)
 int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s);
+// psfr_conv.cu: spectra of nk 41x41 kernels, and the two FFT convolutions of every image
+int run_kernel_spectra(Ctx* c, int nk, const double* kern_dev, double2* khat_dev, cudaStream_t s);
+int run_fft_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s);
 // two Moffat convolutions; img index = draw*nlam + lam
 int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s);
 int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s);

@@ -520,6 +520,8 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
         PSFR_CUDA(c, cudaMemcpyAsync(two, &h2, sizeof(double), cudaMemcpyHostToDevice, s));
         moffat_kernels_kernel<<<ndraw, 256, 0, s>>>(c->d_misc + misc_alpha_tt(c->max_planes), two, 0, c->d_kern_tt);
         PSFR_LAUNCH_CHECK(c);
+        int rc = run_kernel_spectra(c, ndraw, c->d_kern_tt, c->d_khat_tt, s);
+        if (rc) return rc;
     }
     if (mu) {
         // muse_intrinsic_psf (psfrec.py:1160-1168, np.polyval = Horner) and alpha = fwhm/0.2/(2 sqrt(2^(1/beta)-1)) (:923-924)
@@ -542,6 +544,8 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
         PSFR_CUDA(c, cudaStreamSynchronize(s));   // pinned bounce buffer is reused by the caller
         moffat_kernels_kernel<<<nlam, 256, 0, s>>>(d, d + nlam, 1, c->d_kern_mu);
         PSFR_LAUNCH_CHECK(c);
+        int rc = run_kernel_spectra(c, nlam, c->d_kern_mu, c->d_khat_mu, s);
+        if (rc) return rc;
     }
     return PSFR_OK;
 }
@@ -559,15 +563,7 @@ int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s) {
 }
 
 int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s) {
-    const size_t smem = (size_t)(2 * kImg + kKP * kKW) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
-    convolve_kernel<<<ndraw * nlam, 256, smem, s>>>(in_dev, c->d_kern_tt, c->d_kern_mu, nlam, out_dev);
-    PSFR_LAUNCH_CHECK(c);
-    return PSFR_OK;
+    return run_fft_convolve(c, ndraw, nlam, in_dev, out_dev, s);
 }
 
 int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s) {
