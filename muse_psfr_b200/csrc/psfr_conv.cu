@@ -27,9 +27,6 @@ constexpr int kF = 80;            // transform length
 constexpr int kFH = kF / 2 + 1;   // 41 half-spectrum columns
 constexpr int kConvThreads = 256;
 
-struct c2 {
-    double x, y;
-};
 __device__ __forceinline__ double2 cxadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 cxsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cxmul(double2 a, double2 b) {
@@ -95,73 +92,70 @@ __device__ __forceinline__ void dft16s(double2* v) {
 }
 __device__ __forceinline__ constexpr int k1_of_pos(int pos) { return (pos >> 2) + 4 * (pos & 3); }
 
-// pass A on 16 loaded values of sub-sequence n2; result for k1 is written to line slot 5 k1 + n2
-// tw[k] = exp(-2 pi i k / 80)
+// Every pass works in place.  Forward (decimation in time, n = 5 n1 + n2, k = k1 + 16 k2):
+//   pass A (thread n2): 16 slots 5 n1 + n2 -> radix-16 -> Y[n2][k1] in slot 5 k1 + n2
+//   pass B (thread k1): 5 slots 5 k1 + n2, times w80^(n2 k1) -> radix-5 -> X[k1 + 16 k2] in slot 5 k1 + k2
+// so a natural-order line comes out with X[k] in slot P(k) = 5 (k mod 16) + k / 16.
+// Inverse of a P-ordered line (decimation in frequency, n = a + 16 b in slot 5 a + b, k = c + 5 d):
+//   pass B' (thread a): 5 slots 5 a + b -> radix-5 -> times w80^(-a c) -> slot 5 a + c
+//   pass A' (thread c): 16 slots 5 a + c -> radix-16 -> X[c + 5 d] in slot 5 d + c, i.e. natural order.
+// No staging registers, one barrier per pass, stride-5 / unit-stride addressing only.
+__device__ __forceinline__ constexpr int perm_p(int k) { return 5 * (k & 15) + (k >> 4); }
+
+// radix-16 over 16 loaded values; output index j = k1_of_pos(pos) is stored at base[j * stride5 + off]
 template <int SGN>
-__device__ __forceinline__ void pass_a(double2* v, int n2, const double2* tw, double2* line, int stride) {
+__device__ __forceinline__ void pass16(double2* v, double2* base, int stride) {
     dft16s<SGN>(v);
 #pragma unroll
-    for (int pos = 0; pos < 16; ++pos) {
-        const int k1 = k1_of_pos(pos);
-        double2 w = tw[n2 * k1];
-        if (SGN > 0) w.y = -w.y;
-        line[(5 * k1 + n2) * stride] = cxmul(v[pos], w);
-    }
+    for (int pos = 0; pos < 16; ++pos) base[k1_of_pos(pos) * stride] = v[pos];
 }
+
+// z * w80^(SGN e), tw[e] = exp(-2 pi i e / 80)
+template <int SGN>
+__device__ __forceinline__ double2 twmul(double2 z, const double2* tw, int e) {
+    double2 w = tw[e];
+    if (SGN > 0) w.y = -w.y;
+    return cxmul(z, w);
+}
+
+constexpr int kIST = kKW;      // row stride of the real plane: odd, so a column of rows spreads over the banks
+constexpr int kLS = kF + 1;    // stride of the row-pass scratch lines (odd number of 16-byte slots)
 
 struct ConvSmem {
     double2 W[kF * kFH];     // half spectrum / scratch lines
-    double img[kKW * kKW];   // real plane (40x40) or kernel (41x41)
+    double img[kKW * kKW];   // real plane (40x40, stride 41) or kernel (41x41)
     double2 tw[kF];
 };
 
-// ---- rows, forward: real rows (2p, 2p+1) of img[nin][nin] -> W[r][kx]
+// ---- rows, forward: real rows (p, p + NP) of img packed in one transform -> half spectra W[r][kx]
 template <int NIN>
-__device__ void rows_forward(ConvSmem& S) {
+__device__ __noinline__ void rows_forward(ConvSmem& S) {
     constexpr int NP = (NIN + 1) / 2;   // row pairs
     const int tid = threadIdx.x;
-    // pass A: item (p, n2); the 82-slot block of W rows (2p, 2p+1) is the scratch line
     for (int it = tid; it < NP * 5; it += kConvThreads) {
         const int p = it % NP, n2 = it / NP;
-        const int r = 2 * p;
-        const bool has2 = r + 1 < NIN;
+        const bool has2 = p + NP < NIN;
         double2 v[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
             const int n = 5 * n1 + n2;
-            v[n1] = n < NIN ? make_double2(S.img[r * NIN + n], has2 ? S.img[(r + 1) * NIN + n] : 0.0)
+            v[n1] = n < NIN ? make_double2(S.img[p * kIST + n], has2 ? S.img[(p + NP) * kIST + n] : 0.0)
                             : make_double2(0.0, 0.0);
         }
-        pass_a<-1>(v, n2, S.tw, S.W + r * kFH, 1);
+        pass16<-1>(v, S.W + p * kLS + n2, 5);
     }
     __syncthreads();
-    // pass B: item (p, k1): Z[k1 + 16 k2]; all loads, barrier, all stores (in-place line)
-    constexpr int RB = (NP * 16 + kConvThreads - 1) / kConvThreads;
-    double2 z[RB][5];
-#pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < NP * 16) {
-            const int p = it % NP, k1 = it / NP;
-            const double2* line = S.W + 2 * p * kFH;
-#pragma unroll
-            for (int n2 = 0; n2 < 5; ++n2) z[rd][n2] = line[5 * k1 + n2];
-        }
+    for (int it = tid; it < NP * 16; it += kConvThreads) {
+        const int p = it % NP, k1 = it / NP;
+        double2* line = S.W + p * kLS + 5 * k1;
+        double2 z0 = line[0], z1 = twmul<-1>(line[1], S.tw, k1), z2 = twmul<-1>(line[2], S.tw, 2 * k1),
+                z3 = twmul<-1>(line[3], S.tw, 3 * k1), z4 = twmul<-1>(line[4], S.tw, 4 * k1);
+        dft5s<-1>(z0, z1, z2, z3, z4);
+        line[0] = z0, line[1] = z1, line[2] = z2, line[3] = z3, line[4] = z4;     // Z[k1 + 16 k2] in slot 5 k1 + k2
     }
     __syncthreads();
-#pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < NP * 16) {
-            const int p = it % NP, k1 = it / NP;
-            double2* line = S.W + 2 * p * kFH;
-            dft5s<-1>(z[rd][0], z[rd][1], z[rd][2], z[rd][3], z[rd][4]);
-#pragma unroll
-            for (int k2 = 0; k2 < 5; ++k2) line[k1 + 16 * k2] = z[rd][k2];
-        }
-    }
-    __syncthreads();
-    // untangle: A[kx] = (Z[kx] + conj Z[-kx]) / 2 -> row 2p, B[kx] = (Z[kx] - conj Z[-kx]) / 2i -> row 2p+1
+    // untangle: A[kx] = (Z[kx] + conj Z[-kx]) / 2 -> row p, B[kx] = (Z[kx] - conj Z[-kx]) / 2i -> row p + NP
+    // (the target rows overlap other pairs' scratch lines: all loads, barrier, all stores)
     constexpr int RU = (NP * kFH + kConvThreads - 1) / kConvThreads;
     double2 za[RU], zb[RU];
 #pragma unroll
@@ -169,9 +163,9 @@ __device__ void rows_forward(ConvSmem& S) {
         const int it = tid + rd * kConvThreads;
         if (it < NP * kFH) {
             const int kx = it % kFH, p = it / kFH;
-            const double2* line = S.W + 2 * p * kFH;
-            za[rd] = line[kx];
-            zb[rd] = line[(kF - kx) % kF];
+            const double2* line = S.W + p * kLS;
+            za[rd] = line[perm_p(kx)];
+            zb[rd] = line[perm_p((kF - kx) % kF)];
         }
     }
     __syncthreads();
@@ -180,18 +174,18 @@ __device__ void rows_forward(ConvSmem& S) {
         const int it = tid + rd * kConvThreads;
         if (it < NP * kFH) {
             const int kx = it % kFH, p = it / kFH;
-            double2* line = S.W + 2 * p * kFH;
-            line[kx] = make_double2(0.5 * (za[rd].x + zb[rd].x), 0.5 * (za[rd].y - zb[rd].y));
-            if (2 * p + 1 < NIN) line[kFH + kx] = make_double2(0.5 * (za[rd].y + zb[rd].y), 0.5 * (zb[rd].x - za[rd].x));
+            S.W[p * kFH + kx] = make_double2(0.5 * (za[rd].x + zb[rd].x), 0.5 * (za[rd].y - zb[rd].y));
+            if (p + NP < NIN)
+                S.W[(p + NP) * kFH + kx] = make_double2(0.5 * (za[rd].y + zb[rd].y), 0.5 * (zb[rd].x - za[rd].x));
         }
     }
     __syncthreads();
 }
 
-// ---- columns: forward transform of W[0..NIN)[kx] (rows >= NIN are zero) into W[ky][kx], optionally
-// times khat[ky][kx]
+// ---- columns, forward: W[0..NIN)[kx] (rows >= NIN are zero) -> spectrum; ky ends up in row P(ky).
+// MUL: times khat[ky][kx], kept in shared memory; otherwise written to gout[ky][kx] in natural order.
 template <int NIN, bool MUL>
-__device__ void cols_forward(ConvSmem& S, const double2* __restrict__ khat) {
+__device__ __noinline__ void cols_forward(ConvSmem& S, const double2* __restrict__ khat, double2* __restrict__ gout) {
     const int tid = threadIdx.x;
     for (int it = tid; it < kFH * 5; it += kConvThreads) {
         const int kx = it % kFH, n2 = it / kFH;
@@ -201,87 +195,63 @@ __device__ void cols_forward(ConvSmem& S, const double2* __restrict__ khat) {
             const int n = 5 * n1 + n2;
             v[n1] = n < NIN ? S.W[n * kFH + kx] : make_double2(0.0, 0.0);
         }
-        pass_a<-1>(v, n2, S.tw, S.W + kx, kFH);
+        pass16<-1>(v, S.W + n2 * kFH + kx, 5 * kFH);
     }
     __syncthreads();
-    constexpr int RB = (kFH * 16 + kConvThreads - 1) / kConvThreads;
-    double2 z[RB][5];
+    for (int it = tid; it < kFH * 16; it += kConvThreads) {
+        const int kx = it % kFH, k1 = it / kFH;
+        double2* col = S.W + (5 * k1) * kFH + kx;
+        double2 z[5], kh[5];
 #pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < kFH * 16) {
-            const int kx = it % kFH, k1 = it / kFH;
-#pragma unroll
-            for (int n2 = 0; n2 < 5; ++n2) z[rd][n2] = S.W[(5 * k1 + n2) * kFH + kx];
+        for (int q = 0; q < 5; ++q) {
+            z[q] = q ? twmul<-1>(col[q * kFH], S.tw, q * k1) : col[0];
+            if (MUL) kh[q] = __ldg(khat + (k1 + 16 * q) * kFH + kx);
         }
-    }
-    __syncthreads();
+        dft5s<-1>(z[0], z[1], z[2], z[3], z[4]);
 #pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < kFH * 16) {
-            const int kx = it % kFH, k1 = it / kFH;
-            dft5s<-1>(z[rd][0], z[rd][1], z[rd][2], z[rd][3], z[rd][4]);
-#pragma unroll
-            for (int k2 = 0; k2 < 5; ++k2) {
-                const int ky = k1 + 16 * k2;
-                S.W[ky * kFH + kx] = MUL ? cxmul(z[rd][k2], __ldg(khat + ky * kFH + kx)) : z[rd][k2];
-            }
+        for (int k2 = 0; k2 < 5; ++k2) {
+            if (MUL) col[k2 * kFH] = cxmul(z[k2], kh[k2]);
+            else gout[(k1 + 16 * k2) * kFH + kx] = z[k2];
         }
     }
     __syncthreads();
 }
 
-// ---- columns, inverse: W[ky][kx] -> rows 20..59 of the result stored at W[0..40)[kx]
-__device__ void cols_inverse(ConvSmem& S) {
+// ---- columns, inverse (decimation in frequency): spectrum with ky in row P(ky) -> spatial row y in row y
+__device__ __noinline__ void cols_inverse(ConvSmem& S) {
     const int tid = threadIdx.x;
+    for (int it = tid; it < kFH * 16; it += kConvThreads) {
+        const int kx = it % kFH, a = it / kFH;
+        double2* col = S.W + (5 * a) * kFH + kx;
+        double2 z[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) z[q] = col[q * kFH];
+        dft5s<1>(z[0], z[1], z[2], z[3], z[4]);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) col[c * kFH] = c ? twmul<1>(z[c], S.tw, a * c) : z[0];
+    }
+    __syncthreads();
     for (int it = tid; it < kFH * 5; it += kConvThreads) {
-        const int kx = it % kFH, n2 = it / kFH;
+        const int kx = it % kFH, c = it / kFH;
         double2 v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) v[n1] = S.W[(5 * n1 + n2) * kFH + kx];
-        pass_a<1>(v, n2, S.tw, S.W + kx, kFH);
-    }
-    __syncthreads();
-    constexpr int RB = (kFH * 16 + kConvThreads - 1) / kConvThreads;
-    double2 z[RB][5];
-#pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < kFH * 16) {
-            const int kx = it % kFH, k1 = it / kFH;
-#pragma unroll
-            for (int n2 = 0; n2 < 5; ++n2) z[rd][n2] = S.W[(5 * k1 + n2) * kFH + kx];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rd = 0; rd < RB; ++rd) {
-        const int it = tid + rd * kConvThreads;
-        if (it < kFH * 16) {
-            const int kx = it % kFH, k1 = it / kFH;
-            dft5s<1>(z[rd][0], z[rd][1], z[rd][2], z[rd][3], z[rd][4]);
-#pragma unroll
-            for (int k2 = 0; k2 < 5; ++k2) {
-                const int y = k1 + 16 * k2;
-                if (y >= kPSF / 2 && y < kPSF / 2 + kPSF) S.W[(y - kPSF / 2) * kFH + kx] = z[rd][k2];
-            }
-        }
+        for (int a = 0; a < 16; ++a) v[a] = S.W[(5 * a + c) * kFH + kx];
+        pass16<1>(v, S.W + c * kFH + kx, 5 * kFH);       // y = c + 5 d -> row 5 d + c
     }
     __syncthreads();
 }
 
-// ---- rows, inverse: half spectra of rows (2p, 2p+1) -> real rows, columns 20..59, times scale
-__device__ void rows_inverse(ConvSmem& S, double scale) {
-    constexpr int NP = kPSF / 2;
+// ---- rows, inverse: half spectra of output rows (p, p + 20), i.e. rows y = p + 20 and p + 40 of the
+// full convolution -> two real rows, columns 20..59, times scale
+__device__ __noinline__ void rows_inverse(ConvSmem& S, double scale) {
+    constexpr int NP = kPSF / 2, OFF = kPSF / 2;
     const int tid = threadIdx.x;
-    // pass A (all items fit one round): loads from rows 2p / 2p+1, barrier, stores into the same block
     double2 v[16];
     const int p = tid % NP, n2 = tid / NP;
     const bool active = tid < NP * 5;
     if (active) {
-        const double2* A = S.W + 2 * p * kFH;
-        const double2* B = A + kFH;
+        const double2* A = S.W + (p + OFF) * kFH;
+        const double2* B = S.W + (p + NP + OFF) * kFH;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
             const int n = 5 * n1 + n2;
@@ -294,22 +264,22 @@ __device__ void rows_inverse(ConvSmem& S, double scale) {
             }
         }
     }
-    __syncthreads();
-    if (active) pass_a<1>(v, n2, S.tw, S.W + 2 * p * kFH, 1);
+    __syncthreads();   // the scratch lines overlap rows other pairs still read
+    if (active) pass16<1>(v, S.W + p * kLS + n2, 5);
     __syncthreads();
     for (int it = tid; it < NP * 16; it += kConvThreads) {
         const int pp = it % NP, k1 = it / NP;
-        const double2* line = S.W + 2 * pp * kFH;
-        double2 z[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) z[q] = line[5 * k1 + q];
-        dft5s<1>(z[0], z[1], z[2], z[3], z[4]);
+        const double2* line = S.W + pp * kLS + 5 * k1;
+        double2 z0 = line[0], z1 = twmul<1>(line[1], S.tw, k1), z2 = twmul<1>(line[2], S.tw, 2 * k1),
+                z3 = twmul<1>(line[3], S.tw, 3 * k1), z4 = twmul<1>(line[4], S.tw, 4 * k1);
+        dft5s<1>(z0, z1, z2, z3, z4);
+        const double2 z[5] = {z0, z1, z2, z3, z4};
 #pragma unroll
         for (int k2 = 0; k2 < 5; ++k2) {
             const int x = k1 + 16 * k2;
-            if (x >= kPSF / 2 && x < kPSF / 2 + kPSF) {
-                S.img[(2 * pp) * kPSF + x - kPSF / 2] = scale * z[k2].x;
-                S.img[(2 * pp + 1) * kPSF + x - kPSF / 2] = scale * z[k2].y;
+            if (x >= OFF && x < OFF + kPSF) {
+                S.img[pp * kIST + x - OFF] = scale * z[k2].x;
+                S.img[(pp + NP) * kIST + x - OFF] = scale * z[k2].y;
             }
         }
     }
@@ -334,11 +304,10 @@ kernel_spectrum_kernel(const double* __restrict__ kern, double2* __restrict__ kh
     for (int i = threadIdx.x; i < kKW * kKW; i += kConvThreads) S.img[i] = kern[(size_t)k * kKW * kKW + i];
     __syncthreads();
     rows_forward<kKW>(S);
-    cols_forward<kKW, false>(S, nullptr);
-    for (int i = threadIdx.x; i < kF * kFH; i += kConvThreads) khat[(size_t)k * kF * kFH + i] = S.W[i];
+    cols_forward<kKW, false>(S, nullptr, khat + (size_t)k * kF * kFH);
 }
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 3)
 fft_convolve_kernel(const double* __restrict__ in, const double2* __restrict__ khat_tt,
                     const double2* __restrict__ khat_mu, int nlam, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char conv_smem_raw[];
@@ -346,18 +315,18 @@ fft_convolve_kernel(const double* __restrict__ in, const double2* __restrict__ k
     const int img = blockIdx.x, draw = img / nlam, lam = img % nlam;
     constexpr int kImg = kPSF * kPSF;
     load_twiddles(S);
-    for (int i = threadIdx.x; i < kImg; i += kConvThreads) S.img[i] = in[(size_t)img * kImg + i];
+    for (int i = threadIdx.x; i < kImg; i += kConvThreads) S.img[(i / kPSF) * kIST + i % kPSF] = in[(size_t)img * kImg + i];
     __syncthreads();
     const double scale = 1.0 / (kF * kF);
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const double2* kh = pass == 0 ? khat_tt + (size_t)draw * kF * kFH : khat_mu + (size_t)lam * kF * kFH;
         rows_forward<kPSF>(S);
-        cols_forward<kPSF, true>(S, kh);
+        cols_forward<kPSF, true>(S, kh, nullptr);
         cols_inverse(S);
         rows_inverse(S, scale);
     }
-    for (int i = threadIdx.x; i < kImg; i += kConvThreads) out[(size_t)img * kImg + i] = S.img[i];
+    for (int i = threadIdx.x; i < kImg; i += kConvThreads) out[(size_t)img * kImg + i] = S.img[(i / kPSF) * kIST + i % kPSF];
 }
 
 }  // namespace
