@@ -380,7 +380,8 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         const double actual = sums[20] - trial[20];
         // near the minimum the cost is flat to rounding: tolerate a noise-level increase so that
         // Gauss-Newton steps keep contracting, and stop on the (column-scaled) step size
-        const bool small = dn <= 1e-22 * (xn + 1e-300);            // relative step <= 1e-11
+        // MINPACK (the reference, through mpdaf -> scipy leastsq) stops at a relative step of 1.49e-8
+        const bool small = dn <= 1e-18 * (xn + 1e-300);            // relative step <= 1e-9
         if (isfinite(trial[20]) && actual >= -1e-13 * sums[20]) {
             const double rho = pred > 0.0 ? actual / pred : 1.0;
 #pragma unroll
