@@ -166,6 +166,12 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
+    cudaFree(c->d_cube3); cudaFree(c->d_fit2);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     HotTimer* t = timer_of(c);
     if (t) {
@@ -251,6 +257,13 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_cube, P * LM * kPSF * kPSF));
     CK(dev_alloc(c, &c->d_cube2, P * LM * kPSF * kPSF));
     CK(dev_alloc(c, &c->d_fit, P * LM * PSFR_FIT_NPAR));
+    CK(dev_alloc(c, &c->d_cube3, P * LM * kPSF * kPSF));
+    CK(dev_alloc(c, &c->d_fit2, P * LM * PSFR_FIT_NPAR));
+    CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CKC(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
     CK(dev_alloc(c, &c->d_poly, (size_t)65536));
     c->h_pinned_bytes = 1 << 20;
     CKC(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
@@ -450,9 +463,15 @@ int psfr_compute_batch(psfr_ctx* c, int ndraw, const double* draws, int ndir, co
     c->hot_timed = true;
     const int per_chunk = c->max_planes / ndir;
     const size_t img = (size_t)kPSF * kPSF;
-    bool host_out = false;
-    for (int d0 = 0; d0 < ndraw; d0 += per_chunk) {
+    const bool cube_dev = out_cube && is_device_ptr(out_cube);
+    const bool fit_dev = out_fit && is_device_ptr(out_fit);
+    const bool host_out = (out_cube && !cube_dev) || (out_fit && !fit_dev);
+    // Host outputs leave through a second stream: the results of chunk i are copied out while
+    // chunk i + 1 computes, from staging buffers that alternate between two sets.
+    int chunk = 0;
+    for (int d0 = 0; d0 < ndraw; d0 += per_chunk, ++chunk) {
         const int nd = std::min(per_chunk, ndraw - d0);
+        const int b = chunk & 1;
         rc = upload_draws(c, nd, draws + (size_t)d0 * PSFR_DRAW_NPAR, ndir, s);
         if (rc) break;
         if ((rc = run_psd(c, nd, ndir, ngs, s))) break;
@@ -460,27 +479,35 @@ int psfr_compute_batch(psfr_ctx* c, int ndraw, const double* draws, int ndir, co
         if ((rc = run_pruned_psf(c, nd, ndir, nlam, s))) break;
         if ((rc = run_resample(c, nd * nlam, nlam, c->d_cube, s))) break;
         if ((rc = run_build_kernels(c, nd, nlam, lam.data(), true, false, s))) break;
-        const bool cube_dev = out_cube && is_device_ptr(out_cube);
-        double* conv = cube_dev ? out_cube + (size_t)d0 * nlam * img : c->d_cube2;
-        if ((rc = run_convolve(c, nd, nlam, c->d_cube, conv, s))) break;
-        const bool fit_dev = out_fit && is_device_ptr(out_fit);
-        double* fit = fit_dev ? out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR : c->d_fit;
-        if (out_fit && (rc = run_fit(c, nd * nlam, kPSF, kPSF, conv, fit, s))) break;
-        // host outputs: stream-ordered copies (truly asynchronous into pinned memory); one sync below
-        if (out_cube && !cube_dev) {
-            if (cudaMemcpyAsync(out_cube + (size_t)d0 * nlam * img, conv, (size_t)nd * nlam * img * sizeof(double),
-                                cudaMemcpyDefault, s) != cudaSuccess) { rc = set_error(c, PSFR_E_CUDA, "cube copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-            host_out = true;
+        if (host_out && chunk >= 2 && cudaStreamWaitEvent(s, c->ev_copied[b], 0) != cudaSuccess) {
+            rc = set_error(c, PSFR_E_CUDA, "stream wait failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
         }
-        if (out_fit && !fit_dev) {
-            if (cudaMemcpyAsync(out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR, fit,
-                                (size_t)nd * nlam * PSFR_FIT_NPAR * sizeof(double), cudaMemcpyDefault, s) != cudaSuccess) { rc = set_error(c, PSFR_E_CUDA, "fit copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-            host_out = true;
+        double* conv = cube_dev ? out_cube + (size_t)d0 * nlam * img : (b ? c->d_cube3 : c->d_cube2);
+        if ((rc = run_convolve(c, nd, nlam, c->d_cube, conv, s))) break;
+        double* fit = fit_dev ? out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR : (b ? c->d_fit2 : c->d_fit);
+        if (out_fit && (rc = run_fit(c, nd * nlam, kPSF, kPSF, conv, fit, s))) break;
+        if (host_out) {
+            cudaError_t e = cudaEventRecord(c->ev_done[b], s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0);
+            if (e == cudaSuccess && out_cube && !cube_dev)
+                e = cudaMemcpyAsync(out_cube + (size_t)d0 * nlam * img, conv, (size_t)nd * nlam * img * sizeof(double),
+                                    cudaMemcpyDefault, c->copy_stream);
+            if (e == cudaSuccess && out_fit && !fit_dev)
+                e = cudaMemcpyAsync(out_fit + (size_t)d0 * nlam * PSFR_FIT_NPAR, fit,
+                                    (size_t)nd * nlam * PSFR_FIT_NPAR * sizeof(double), cudaMemcpyDefault, c->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_copied[b], c->copy_stream);
+            if (e != cudaSuccess) {
+                rc = set_error(c, PSFR_E_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+                break;
+            }
         }
     }
     c->hot_timed = false;
     if (host_out) {
-        cudaError_t e = cudaStreamSynchronize(s);
+        // host outputs are complete on return; later work on `s` must not overtake the copies
+        cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess && !rc) rc = set_error(c, PSFR_E_CUDA, "compute_batch: %s", cudaGetErrorString(e));
     }
     return rc;

@@ -79,7 +79,12 @@ struct Ctx {
     double2* d_khat_mu = nullptr; // [max_lambda][80][41] half spectra of the MUSE kernels
     double* d_cube = nullptr;    // [max_planes*max_lambda][40][40] staging for cubes
     double* d_cube2 = nullptr;   // second staging buffer
+    double* d_cube3 = nullptr;   // third staging buffer (double-buffered device -> host copies)
     double* d_fit = nullptr;     // [max_planes*max_lambda][PSFR_FIT_NPAR]
+    double* d_fit2 = nullptr;    // second fit buffer (double-buffered device -> host copies)
+    cudaStream_t copy_stream = nullptr;      // device -> host copies of finished chunks
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};    // chunk results ready (compute stream)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // chunk results copied out (copy stream)
     double* d_stage = nullptr;   // generic staging for host inputs (max_planes*N*N doubles)
     double* d_poly = nullptr;    // polynomial fit scratch
     void* h_pinned = nullptr;    // pinned bounce buffer
