@@ -1,8 +1,7 @@
 // Per-image tail of the path, one CTA per 40 x 40 image:
 //   resample_kernel : clip >= 0, bilinear 80x80 samples -> 40x40, per-plane normalisation
 //                     (psf_muse tail, psfrec.py:679-685 with interpolate :635-641)
-//   convolve_kernel : tip-tilt Moffat (beta = 2) then MUSE intrinsic Moffat, each a
-//                     zero-padded 'same' linear convolution (convolve_final_psf, :911-930)
+//   (the two Moffat convolutions of convolve_final_psf live in psfr_conv.cu)
 //   fit_kernel      : 5-parameter circular Moffat least squares by Levenberg-Marquardt with
 //                     analytic Jacobian (fit_psf_cube -> mpdaf moffat_fit, :861-871)
 //   mean / polyfit  : time mean of cubes (:1104) and polynomial smoothing (:1174-1210)
@@ -78,75 +77,6 @@ resample_kernel(const double* __restrict__ samp, const double* __restrict__ frac
     cnt = 0;
     for (int idx = threadIdx.x; idx < kImg; idx += blockDim.x, ++cnt)
         cube[(size_t)img * kImg + idx] = vals[cnt] / tot;
-}
-
-// ---------------------------------------------------------------- convolution
-// out[i][j] = sum_{i',j'} in[i'][j'] K[i-i'+20][j-j'+20]  (scipy fftconvolve(..., 'same') with a
-// 41x41 kernel = zero-padded linear convolution cropped to the input frame).
-// Thread (ib, j) owns 8 output rows i0..i0+7 of column j; for a fixed input column j' the
-// kernel column K[.][j-j'+20] slides through a register window as i' advances, so each
-// step costs one broadcast load, one kernel load and 8 FMAs.
-constexpr int kKP = 79;  // padded kernel rows: index di + 19, di = i - i' + 20 in [-19, 59]
-
-__device__ void conv_same(const double* __restrict__ in, const double* __restrict__ kp,
-                          double* __restrict__ out) {
-    const int tid = threadIdx.x;
-    if (tid < 5 * kPSF) {
-        const int ib = tid / kPSF, j = tid % kPSF, i0 = 8 * ib;
-        double acc[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-        for (int jp = 0; jp < kPSF; ++jp) {
-            const int dj = j - jp + 20;
-            if (dj < 0 || dj > 40) continue;
-            const double* kc = kp + dj;             // column dj of the padded kernel, row stride 41
-            // window w[u] = Kpad[i0 + u - i' + 20 + 19][dj]; start at i' = 0
-            double w[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = kc[(i0 + u + 39) * kKW];
-#pragma unroll
-            for (int ip = 0; ip < kPSF; ++ip) {
-                const double pv = in[ip * kPSF + jp];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] = fma(pv, w[u], acc[u]);
-                if (ip + 1 < kPSF) {
-#pragma unroll
-                    for (int u = 7; u > 0; --u) w[u] = w[u - 1];
-                    w[0] = kc[(i0 + 39 - (ip + 1)) * kKW];
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) out[(i0 + u) * kPSF + j] = acc[u];
-    }
-}
-
-// load a 41x41 kernel into the zero-padded [79][41] layout
-__device__ void load_kernel_padded(const double* __restrict__ k, double* __restrict__ kp) {
-    for (int idx = threadIdx.x; idx < kKP * kKW; idx += blockDim.x) {
-        const int r = idx / kKW - 19;
-        kp[idx] = (r >= 0 && r < kKW) ? k[r * kKW + idx % kKW] : 0.0;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-convolve_kernel(const double* __restrict__ in, const double* __restrict__ ktt,
-                const double* __restrict__ kmu, int nlam, double* __restrict__ out) {
-    extern __shared__ double dyn_smem[];
-    double* a = dyn_smem;               // kImg
-    double* b = a + kImg;               // kImg
-    double* kp = b + kImg;              // kKP*kKW
-    const int img = blockIdx.x, draw = img / nlam, lam = img % nlam;
-    for (int i = threadIdx.x; i < kImg; i += blockDim.x) a[i] = in[(size_t)img * kImg + i];
-    load_kernel_padded(ktt + (size_t)draw * kKW * kKW, kp);
-    __syncthreads();
-    conv_same(a, kp, b);
-    __syncthreads();
-    load_kernel_padded(kmu + (size_t)lam * kKW * kKW, kp);
-    __syncthreads();
-    conv_same(b, kp, a);
-    __syncthreads();
-    for (int i = threadIdx.x; i < kImg; i += blockDim.x) out[(size_t)img * kImg + i] = a[i];
 }
 
 // ---------------------------------------------------------------- Moffat fit

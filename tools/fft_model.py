@@ -22,7 +22,7 @@ def conflicts(addrs):
     return wf
 
 
-def model(N, S1pad=4, S2=None, verbose=True):
+def model(N, S1pad=2, S2=None, verbose=True):
     R3 = N // 64
     TL = N // 40
     NQ = 64 // TL                      # (k1,k2) pairs per lane in pass 3
@@ -59,7 +59,7 @@ def model(N, S1pad=4, S2=None, verbose=True):
             addrs = []
             for t in range(TL):
                 p = t + TL * jp
-                k1, n3 = divmod(p, R3)
+                n3, k1 = divmod(p, 8)
                 addrs.append(k1 * S1 + n2 * R3 + n3)
             wf_r1 += conflicts(addrs)
             for t in range(TL):
@@ -68,26 +68,26 @@ def model(N, S1pad=4, S2=None, verbose=True):
     for t in range(TL):
         for jp in range(5):
             p = t + TL * jp
-            k1, n3 = divmod(p, R3)
+            n3, k1 = divmod(p, 8)
             blk = v[t, jp * 8:(jp + 1) * 8].copy()
             for k2 in range(8):
                 v[t, jp * 8 + k2] = sum(blk[n2] * w(8, n2 * k2) for n2 in range(8)) * w(N // 8, n3 * k2)
     # exchange 2
-    sm = np.zeros(64 * S2 + 64, complex)
+    sm = np.zeros(64 * R3 + 64, complex)
     wf_w2 = wf_r2 = 0
     for jp in range(5):
         for k2 in range(8):
             addrs = []
             for t in range(TL):
                 p = t + TL * jp
-                k1, n3 = divmod(p, R3)
-                addrs.append((k1 + 8 * k2) * S2 + n3)
+                n3, k1 = divmod(p, 8)
+                addrs.append(64 * n3 + ((k1 + 8 * k2) ^ (8 * (n3 & 1))))
             wf_w2 += conflicts(addrs)
             for t in range(TL):
                 sm[addrs[t]] = v[t, jp * 8 + k2]
     for u in range(NQ):
         for n3 in range(R3):
-            addrs = [(t + TL * u) * S2 + n3 for t in range(TL)]
+            addrs = [64 * n3 + ((t + TL * u) ^ (8 * (n3 & 1))) for t in range(TL)]
             wf_r2 += conflicts(addrs)
             for t in range(TL):
                 v[t, u * R3 + n3] = sm[addrs[t]]
@@ -103,14 +103,11 @@ def model(N, S1pad=4, S2=None, verbose=True):
     err = np.abs(X - ref).max() / np.abs(ref).max()
     ideal = lambda n: n * max(1, TL // 16)
     if verbose:
-        print(f'N={N} R3={R3} TL={TL} S1={S1} S2={S2} err={err:.2e} '
+        print(f'N={N} R3={R3} TL={TL} S1={S1} err={err:.2e} '
               f'wavefronts w1={wf_w1}/{ideal(40)} r1={wf_r1}/{ideal(40)} '
               f'w2={wf_w2}/{ideal(40)} r2={wf_r2}/{ideal(40)}')
     return err, (wf_w1, wf_r1, wf_w2, wf_r2)
 
 
 if __name__ == '__main__':
-    for N in (1280, 2560, 640, 320):
-        model(N)
-    for S2 in range(20, 40):
-        model(1280, S2=S2)
+    model(1280)
