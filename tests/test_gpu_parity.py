@@ -375,6 +375,76 @@ def test_batch_is_independent_of_chunking(psfrec):
 
 
 # ---------------------------------------------------------------- mean + refit, polynomials (a12, a13)
+def test_single_draw_single_wavelength(psfrec):
+    """Smallest possible call: one draw, one wavelength (every ring / counter path with one item)."""
+    lam = np.array([653.])
+    fit, cube = psfrec.compute_psf_batch(lam, [0.83], [0.61], [17.5])
+    ref, ref_cube = orc.compute_psf(lam, 0.83, 0.61, 17.5)
+    assert cube.shape == (1, 1, 40, 40)
+    assert_image_close(cube[0, 0], ref_cube[0])
+    from muse_psfr_b200 import _lib
+    assert_allclose(fit[0, :, _lib.FIT_FWHM] * 0.2, ref['fwhm'], rtol=FIT_RTOL)
+
+
+def test_device_buffers_equal_host_buffers(psfrec):
+    """The C ABI takes host or device pointers: torch tensors as plain device buffers give the
+    bit-identical result of the host-buffer call (and exercise the no-copy output path)."""
+    import torch
+    from muse_psfr_b200 import _lib
+    lam = LBDA35[::9]
+    s, g, l0 = np.array([0.7, 1.2, 1.6]), np.array([0.8, 0.6, 0.45]), np.array([12., 22., 27.])
+    fit_h, cube_h = psfrec.compute_psf_batch(lam, s, g, l0)
+    recs = np.stack([psfrec.draw_record([g[i], 1 - g[i]], (100, 10000), s[i], l0[i], 0.,
+                                        alpha_tt=psfrec.tiptilt_alpha(s[i], g[i], l0[i])) for i in range(3)])
+    d_recs = torch.from_numpy(recs).cuda()
+    d_cube = torch.empty((3, lam.size, 40, 40), dtype=torch.float64, device='cuda')
+    d_fit = torch.empty((3, lam.size, _lib.FIT_NPAR), dtype=torch.float64, device='cuda')
+    ctx = psfrec.get_context(max_planes=16, max_lambda=35)
+    ctx.compute_batch(d_recs, psfrec.direction_perf(1), psfrec._lgs_positions(False), lam, out_cube=d_cube,
+                      out_fit=d_fit, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_cube.cpu().numpy(), cube_h)
+    assert np.array_equal(d_fit.cpu().numpy(), fit_h)
+
+
+def test_c_abi_argument_errors(psfrec):
+    """Error behaviour of the boundary: negative codes + message, never a crash or a fallback."""
+    from muse_psfr_b200 import _lib
+    ctx = psfrec.get_context()
+    lib = _lib.load()
+    recs = np.zeros((1, _lib.DRAW_NPAR))
+    recs[0, _lib.DRAW_NLAYERS] = 3                       # the reference raises ValueError for 3 layers
+    dirs, pos, lam = _lib.f64(psfrec.direction_perf(1)), _lib.f64(psfrec._lgs_positions(False)), np.array([500.])
+    out = np.empty((1, 1, 40, 40))
+    rc = lib.psfr_compute_batch(ctx._h, 1, _lib.ptr(recs), 1, _lib.ptr(dirs), 4, _lib.ptr(pos), 1, _lib.ptr(lam),
+                                _lib.ptr(out), None, None)
+    assert rc == _lib.E_UNSUPPORTED and b'layers' in lib.psfr_last_error(ctx._h)
+    rc = lib.psfr_compute_batch(ctx._h, 0, _lib.ptr(recs), 1, _lib.ptr(dirs), 4, _lib.ptr(pos), 1, _lib.ptr(lam),
+                                _lib.ptr(out), None, None)
+    assert rc in (_lib.E_ARG, _lib.E_CAPACITY)
+    assert lib.psfr_compute_batch(ctx._h, 1, None, 1, _lib.ptr(dirs), 4, _lib.ptr(pos), 1, _lib.ptr(lam),
+                                  _lib.ptr(out), None, None) == _lib.E_ARG
+    assert lib.psfr_set_option(ctx._h, 99, 1.0) == _lib.E_ARG
+    assert lib.psfr_set_option(ctx._h, _lib.OPT_EXP_CUT, -1.0) == _lib.E_ARG
+    assert lib.psfr_psf_cube(ctx._h, 1, 1, ctx.max_lambda + 1, _lib.ptr(np.full(ctx.max_lambda + 1, 600.)),
+                             _lib.ptr(out), None) < 0
+    with pytest.raises(_lib.PsfrError):
+        ctx.psd_to_psf(0, -1.0, np.empty((1280, 1280)))
+
+
+def test_config5_field_grid(psfrec):
+    """dim 2560 with a 2 x 2 field grid in three-LGS mode: direction mean inside the column
+    kernel on the two-transform (NF = 2) path, against the oracle."""
+    kw = dict(npsflin=2, dim=2560, three_lgs_mode=True)
+    psd = psfrec.simul_psd_wfm([0.6, 0.4], (200, 9000), 0.9, 20., verbose=False, **kw)
+    ref_psd = orc.simul_psd_wfm([0.6, 0.4], (200, 9000), 0.9, 20., **kw)
+    assert_allclose(psd, ref_psd, rtol=1e-10, atol=0)
+    lam = np.array([560.])
+    got = psfrec.psf_muse(psd, lam)
+    ref = orc.psf_muse(ref_psd, lam)
+    assert_image_close(got[0], ref[0])
+
+
 def test_mean_refit(psfrec, golden):
     go = golden('oracle_config1')
     from muse_psfr_b200 import _lib
