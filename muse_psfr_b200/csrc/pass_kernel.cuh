@@ -77,12 +77,7 @@ pass_kernel(Loader ld, Storer st, int nfft, const double2* __restrict__ g_tw, co
 
 template <int NF, class Loader, class Storer>
 static int launch_pass(Ctx* c, Loader ld, Storer st, int nfft, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(pass_kernel<NF, Loader, Storer>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem<NF>()));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(c, pass_kernel<NF, Loader, Storer>, pass_smem<NF>())) return rc;
     int grid = (nfft + kPassWarps - 1) / kPassWarps;
     const int cap = c->sm_count * 8;
     if (grid > cap) grid = cap;

@@ -332,24 +332,14 @@ fft_convolve_kernel(const double* __restrict__ in, const double2* __restrict__ k
 }  // namespace
 
 int run_kernel_spectra(Ctx* c, int nk, const double* kern_dev, double2* khat_dev, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(kernel_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(ConvSmem)));
-        attr = true;
-    }
+    if (int rc = ensure_dynamic_smem(c, kernel_spectrum_kernel, sizeof(ConvSmem))) return rc;
     kernel_spectrum_kernel<<<nk, kConvThreads, sizeof(ConvSmem), s>>>(kern_dev, khat_dev);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }
 
 int run_fft_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_dev, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(fft_convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(ConvSmem)));
-        attr = true;
-    }
+    if (int rc = ensure_dynamic_smem(c, fft_convolve_kernel, sizeof(ConvSmem))) return rc;
     fft_convolve_kernel<<<ndraw * nlam, kConvThreads, sizeof(ConvSmem), s>>>(in_dev, c->d_khat_tt, c->d_khat_mu, nlam,
                                                                               out_dev);
     PSFR_LAUNCH_CHECK(c);

@@ -413,12 +413,7 @@ template <int NF>
 static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     using D = Dim<NF>;
     using C = HotCfg<NF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(hot_rows_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)C::Smem));
-        attr_set = true;
-    }
+    if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
     HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_counter,
                 c->exp_cut, nplanes, nlam};
@@ -434,12 +429,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     c->hot_psfs += (long long)nplanes * nlam;
     // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
     // inverse transform); psf_muse averages the directions.
-    static bool attr2_set = false;
-    if (!attr2_set) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(hot_cols_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)ColCfg<NF>::Smem));
-        attr2_set = true;
-    }
+    if ((rc = ensure_dynamic_smem(c, hot_cols_kernel<NF>, ColCfg<NF>::Smem))) return rc;
     ColParams q{c->d_ybuf, c->d_samp, c->d_kidx, c->d_wsamp, ndraw * nlam * (kNS / 2), nlam, ndir, 1.0 / ndir};
     int cgrid = (q.nlines + ColCfg<NF>::Warps - 1) / ColCfg<NF>::Warps;
     if (cgrid > c->sm_count) cgrid = c->sm_count;

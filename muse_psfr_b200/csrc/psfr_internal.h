@@ -95,10 +95,39 @@ struct Ctx {
     long long hot_psfs = 0;
     bool hot_timed = false;
 
+    // kernels whose dynamic shared-memory limit has been raised on THIS device (the attribute is
+    // per device, so a process-wide flag would break a second context on another GPU)
+    const void* smem_funcs[64] = {nullptr};
+    size_t smem_bytes[64] = {0};
+    int n_smem_funcs = 0;
+
     char err[512] = {0};
 };
 
 int set_error(Ctx* c, int code, const char* fmt, ...);
+
+// raise cudaFuncAttributeMaxDynamicSharedMemorySize of `func` to `bytes` once per context
+template <class F>
+inline int ensure_dynamic_smem(Ctx* c, F* func, size_t bytes) {
+    const void* key = reinterpret_cast<const void*>(func);
+    for (int i = 0; i < c->n_smem_funcs; ++i)
+        if (c->smem_funcs[i] == key) {
+            if (c->smem_bytes[i] >= bytes) return PSFR_OK;
+            cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e != cudaSuccess) return set_error(c, PSFR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            c->smem_bytes[i] = bytes;
+            return PSFR_OK;
+        }
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return set_error(c, PSFR_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    if (c->n_smem_funcs < 64) {
+        c->smem_funcs[c->n_smem_funcs] = key;
+        c->smem_bytes[c->n_smem_funcs++] = bytes > 48 * 1024 ? bytes : 48 * 1024;
+    }
+    return PSFR_OK;
+}
 
 #define PSFR_CUDA(ctx, call)                                                             \
     do {                                                                                 \

@@ -483,11 +483,7 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
 
 int run_resample(Ctx* c, int nimg, int nlam, double* cube_dev, cudaStream_t s) {
     const size_t smem = (size_t)(kNS * kNS + 32) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    if (int rc = ensure_dynamic_smem(c, resample_kernel, smem)) return rc;
     resample_kernel<<<nimg, 256, smem, s>>>(c->d_samp, c->d_frac, nlam, cube_dev);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
@@ -500,11 +496,7 @@ int run_convolve(Ctx* c, int ndraw, int nlam, const double* in_dev, double* out_
 int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit_dev, cudaStream_t s) {
     const size_t smem = (size_t)kFitWarps * (ny * nx + nx) * sizeof(double);
     if (smem > 200 * 1024) return set_error(c, PSFR_E_UNSUPPORTED, "image %dx%d too large for the fitter", ny, nx);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        PSFR_CUDA(c, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    if (int rc = ensure_dynamic_smem(c, fit_kernel, smem)) return rc;
     int grid = (nimg + kFitWarps - 1) / kFitWarps;
     const int resident = c->sm_count * 3;            // 166 registers x 128 threads: three CTAs per SM
     if (grid > resident) grid = resident;

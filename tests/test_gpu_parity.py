@@ -445,6 +445,19 @@ def test_config5_field_grid(psfrec):
     assert_image_close(got[0], ref[0])
 
 
+def test_two_devices_in_one_process(psfrec):
+    """One context per GPU inside one process (kernel attributes are per device): the second GPU
+    gives the bit-identical result of the first."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    lam = LBDA35[::12]
+    args = (lam, [0.9, 1.5], [0.7, 0.5], [20., 14.])
+    fit0, cube0 = psfrec.compute_psf_batch(*args, device=0)
+    fit1, cube1 = psfrec.compute_psf_batch(*args, device=1)
+    assert np.array_equal(cube0, cube1) and np.array_equal(fit0, fit1)
+
+
 def test_mean_refit(psfrec, golden):
     go = golden('oracle_config1')
     from muse_psfr_b200 import _lib
