@@ -35,16 +35,18 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link the C-ABI shared library."""
+    """Compile every CUDA source for sm_100a and link the C-ABI shared library.
+    PSFR_NVCC_EXTRA (environment) appends flags, e.g. -DPSFR_HOT_BLK=4 for tuning experiments."""
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
+    extra = os.environ.get('PSFR_NVCC_EXTRA', '').split()
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:

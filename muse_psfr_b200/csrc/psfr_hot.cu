@@ -18,6 +18,10 @@
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 
+#ifndef PSFR_HOT_BLK
+#define PSFR_HOT_BLK 4
+#endif
+
 namespace psfr {
 
 // Launch shape per grid size: the ring stage holds two rows of D and two of the telescope OTF
@@ -180,27 +184,34 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
 #pragma unroll 1
                 for (int sub = 0; sub < NF; ++sub) {
                     double2 v[40];
-                    // two slots (= four independent exp chains) per basic block
+                    // kBlk slots (= 2 kBlk independent exp chains) per basic block
+                    constexpr int kBlk = PSFR_HOT_BLK;
 #pragma unroll
-                    for (int i = 0; i < 40; i += 2) {
-                        const int n0 = slot_e<NF>(i, lane, sub), n1 = slot_e<NF>(i + 1, lane, sub);
-                        const double ta = sT[n0], tb = sT[kN + n0], tc = sT[n1], td = sT[kN + n1];
-                        const double xa = negc * sD[n0], xb_ = negc * sD[kN + n0];
-                        const double xc = negc * sD[n1], xd = negc * sD[kN + n1];
-                        // outside the pupil-autocorrelation support the OTF is exactly zero; below
-                        // the underflow cut it is flushed to zero
-                        const bool dead = (is_zero_bits(ta) | below_cut(xa, cut_hi)) &
-                                          (is_zero_bits(tb) | below_cut(xb_, cut_hi)) &
-                                          (is_zero_bits(tc) | below_cut(xc, cut_hi)) &
-                                          (is_zero_bits(td) | below_cut(xd, cut_hi));
+                    for (int i = 0; i < 40; i += kBlk) {
+                        double tt[2 * kBlk], xx[2 * kBlk];
+                        bool dead = true;
+#pragma unroll
+                        for (int q = 0; q < kBlk; ++q) {
+                            const int n = slot_e<NF>(i + q, lane, sub);
+                            tt[2 * q] = sT[n];
+                            tt[2 * q + 1] = sT[kN + n];
+                            xx[2 * q] = negc * sD[n];
+                            xx[2 * q + 1] = negc * sD[kN + n];
+                            // outside the pupil-autocorrelation support the OTF is exactly zero;
+                            // below the underflow cut it is flushed to zero
+                            dead = dead & (is_zero_bits(tt[2 * q]) | below_cut(xx[2 * q], cut_hi)) &
+                                   (is_zero_bits(tt[2 * q + 1]) | below_cut(xx[2 * q + 1], cut_hi));
+                        }
                         if (__all_sync(0xffffffffu, dead)) {
-                            v[i] = make_double2(0.0, 0.0);
-                            v[i + 1] = make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int q = 0; q < kBlk; ++q) v[i + q] = make_double2(0.0, 0.0);
                         } else {
-                            const double ea = fast_exp(xa), eb = fast_exp(xb_);
-                            const double ec = fast_exp(xc), ed = fast_exp(xd);
-                            v[i] = make_double2(ea * ta, eb * tb);
-                            v[i + 1] = make_double2(ec * tc, ed * td);
+                            double ee[2 * kBlk];
+#pragma unroll
+                            for (int q = 0; q < 2 * kBlk; ++q) ee[q] = fast_exp(xx[q]);
+#pragma unroll
+                            for (int q = 0; q < kBlk; ++q)
+                                v[i + q] = make_double2(ee[2 * q] * tt[2 * q], ee[2 * q + 1] * tt[2 * q + 1]);
                         }
                     }
                     warp_fft<kR3>(v, xb, tw1, tw2, lane);
