@@ -112,8 +112,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # bounded sample: one draw per core, 6 wavelengths each (~2.5 s of work per core per step)
-    nlam, ndraw = 6, cores
+    # bounded sample: one full draw (35 wavelengths, like the GPU arm) per core, ~12 s per step
+    nlam, ndraw = LBDA.size, cores
     times, vals = [], []
     for step in range(args.warmup + args.steps):
         v, dt = cpu_throughput(ndraw, nlam, cores)
@@ -237,9 +237,10 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, dt = cpu_throughput(cores, 6, cores)
+        v, dt = cpu_throughput(cores, nlam, cores)
         cpu = {'value': v, 'unit': 'PSF/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d draws of the same sweep x 6 wavelengths, joblib over draws, numpy oracle (%.1f s)' % (cores, dt)}
+               'sample': '%d draws of the same sweep x %d wavelengths, joblib over draws (one worker per core), '
+                         'numpy oracle port of psfrec.py (%.1f s)' % (cores, nlam, dt)}
     line = {
         'metric': 'PSFs/sec (dim 1280, PSD->PSF->Moffat fit)', 'value': value, 'unit': 'PSF/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
@@ -249,6 +250,7 @@ def run_gpu(args):
                    'draws_per_gpu': nd, 'wavelengths': nlam, 'chunk_planes': args.max_planes,
                    'l2': '256 MB buffer rewritten before every step (inside the timed region); per-chunk '
                          'working set ~4 GB >> 126 MB L2',
+                   'exp_cut': 'OTF entries below exp(-64) = 1.6e-28 of the peak are flushed to zero (DESIGN.md 3.7)',
                    'results_finite': finite},
         'e2e': {'value': e2e, 'unit': 'PSF/s',
                 'h2d_bytes_per_step': int(recs.nbytes + dirs.nbytes + pos.nbytes + LBDA.nbytes),
