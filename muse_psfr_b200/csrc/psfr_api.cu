@@ -160,7 +160,7 @@ const char* psfr_last_error(const psfr_ctx* ctx) { return ctx ? ctx->err : g_cre
 void psfr_destroy(psfr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_pup); cudaFree(c->d_otf); cudaFree(c->d_geom); cudaFree(c->d_psd);
+    cudaFree(c->d_tw); cudaFree(c->d_pup); cudaFree(c->d_otf); cudaFree(c->d_geom); cudaFree(c->d_psd); cudaFree(c->d_psdq);
     cudaFree(c->d_bt); cudaFree(c->d_dphi); cudaFree(c->d_ybuf); cudaFree(c->d_samp); cudaFree(c->d_ao);
     cudaFree(c->d_draws); cudaFree(c->d_misc); cudaFree(c->d_lam); cudaFree(c->d_kidx); cudaFree(c->d_frac);
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
@@ -238,6 +238,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_otf, (size_t)kRows * kN));
     CK(dev_alloc(c, &c->d_geom, (size_t)3 * kAO * kAO));
     CK(dev_alloc(c, &c->d_psd, P * kN * kN));
+    CK(dev_alloc(c, &c->d_psdq, P * kNH * kNH));
     CK(dev_alloc(c, &c->d_bt, P * kN * kRows));
     CK(dev_alloc(c, &c->d_dphi, P * kRows * kN));
     CK(dev_alloc(c, &c->d_dmin, P * kRows));
@@ -474,8 +475,8 @@ int psfr_compute_batch(psfr_ctx* c, int ndraw, const double* draws, int ndir, co
         const int b = chunk & 1;
         rc = upload_draws(c, nd, draws + (size_t)d0 * PSFR_DRAW_NPAR, ndir, s);
         if (rc) break;
-        if ((rc = run_psd(c, nd, ndir, ngs, s))) break;
-        if ((rc = run_structure_function(c, nd * ndir, s))) break;
+        if ((rc = run_psd(c, nd, ndir, ngs, s, false))) break;
+        if ((rc = run_structure_function(c, nd * ndir, s, true, ndir))) break;
         if ((rc = run_pruned_psf(c, nd, ndir, nlam, s))) break;
         if ((rc = run_resample(c, nd * nlam, nlam, c->d_cube, s))) break;
         if ((rc = run_build_kernels(c, nd, nlam, lam.data(), true, false, s))) break;

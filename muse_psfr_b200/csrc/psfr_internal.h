@@ -59,6 +59,7 @@ struct Ctx {
     double* d_otf = nullptr;     // [rows][N] telescope OTF half-plane (centred, pad row zero)
     double* d_geom = nullptr;    // f, f_x, f_y: 3 x 80 x 80
     double* d_psd = nullptr;     // [max_planes][N][N]
+    double* d_psdq = nullptr;    // [max_planes][N/2][N/2] fitting PSD, one mirror quadrant, unscaled (fused path)
     double2* d_bt = nullptr;     // [max_planes][N][rows] transposed row-pass output (full mode)
     double* d_dphi = nullptr;    // [max_planes][rows][N] structure function (transposed half-plane)
     double* d_dmin = nullptr;    // [max_planes][rows] smallest structure-function value of each row
@@ -147,8 +148,9 @@ inline int ensure_dynamic_smem(Ctx* c, F* func, size_t bytes) {
     } while (0)
 
 // ---- psfr_passes.cu: generic row/column FFT passes ----------------------------------
-// stage A (PSD -> D_unit) on planes [0, nplanes) of the workspace
-int run_structure_function(Ctx* c, int nplanes, cudaStream_t s);
+// stage A (PSD -> D_unit) on planes [0, nplanes) of the workspace; from_quadrant: the PSD is the
+// quadrant form (d_psdq + d_ao) written by run_psd(..., full = false) instead of d_psd
+int run_structure_function(Ctx* c, int nplanes, cudaStream_t s, bool from_quadrant = false, int ndir = 1);
 // full-grid stage B: plane `plane`, exponent scale clam -> d_psd-sized output in `out_dev`
 int run_full_psf(Ctx* c, int plane, double clam, double* out_dev, cudaStream_t s);
 // context init: pupil + telescope OTF
@@ -162,7 +164,9 @@ int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_
 int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s);
 
 // ---- psfr_psd.cu ---------------------------------------------------------------------
-int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s);  // uses d_draws, d_misc
+// uses d_draws, d_misc.  full: write the N x N PSD of every plane into d_psd (simul_psd_wfm);
+// otherwise only the AO zones (d_ao) and one mirror quadrant of the fitting PSD (d_psdq)
+int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s, bool full = true);
 
 // ---- psfr_plane.cu -------------------------------------------------------------------
 int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host, bool tt, bool mu,

@@ -40,6 +40,41 @@ struct LoadEvenRows {
     }
 };
 
+// The same even-part rows from the quadrant form of the PSD (fused path): P[a][n] =
+// max(fit, AO zone) * scale2 with fit = Q[min(a, N-1-a)][min(n, N-1-n)] of the plane's draw.
+template <int NF>
+struct LoadEvenRowsQuad {
+    using D = Dim<NF>;
+    const double* Q;    // [ndraw][N/2][N/2] unscaled fitting PSD
+    const double* ao;   // [nplanes][80][80] AO zones (centred, reference orientation), unscaled
+    int ndir;
+    double scale2;
+    __device__ __forceinline__ double psd(const double* q, const double* z, int a, int n) const {
+        const int qa = a < D::NH ? a : D::N - 1 - a, qn = n < D::NH ? n : D::N - 1 - n;
+        double val = __ldg(q + (size_t)qa * D::NH + qn);
+        constexpr int lo = D::NH - kAO / 2, hi = D::NH + kAO / 2;
+        if (a >= lo && a < hi && n >= lo && n < hi) val = fmax(val, __ldg(z + (a - lo) * kAO + (n - lo)));
+        return __dmul_rn(val, scale2);   // never contracted into the sum below: same rounding as the stored PSD
+    }
+    __device__ void operator()(int f, int lane, double2* v, int sub) const {
+        const int plane = f / D::Pairs, rp = f % D::Pairs;
+        const int a1 = 2 * rp, a2 = a1 + 1;
+        const double* q = Q + (size_t)(plane / ndir) * D::NH * D::NH;
+        const double* z = ao + (size_t)plane * kAO * kAO;
+        const int a1m = (D::N - a1) % D::N;
+        const bool ok2 = a2 <= D::NH;
+        const int a2m = ok2 ? D::N - a2 : 0;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_e<NF>(i, lane, sub);
+            const int nm = (D::N - n) % D::N;
+            const double e1 = 0.5 * (psd(q, z, a1, n) + psd(q, z, a1m, nm));
+            const double e2 = ok2 ? 0.5 * (psd(q, z, a2, n) + psd(q, z, a2m, nm)) : 0.0;
+            v[i] = make_double2(e1, e2);
+        }
+    }
+};
+
 // rows (2f, 2f+1) of exp(-c D) * OTF on the transposed half-plane (psfrec.py:793-797)
 template <int NF>
 struct LoadOtfRows {
@@ -264,11 +299,15 @@ __global__ void finalize_otf_kernel(double* t, size_t live, size_t total, double
 
 // ------------------------------------------------------------------ drivers
 template <int NF>
-static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s) {
+static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_quadrant, int ndir) {
     using D = Dim<NF>;
     // pass 1: rows of the even part of the PSD -> transposed half spectrum
-    int rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
-                             nplanes * D::Pairs, s);
+    const double k = 0.5 * 1000 / (2 * 3.141592653589793);      // rad^2 -> nm^2 (psfrec.py:151), as run_psd
+    int rc = from_quadrant
+                 ? launch_pass<NF>(c, LoadEvenRowsQuad<NF>{c->d_psdq, c->d_ao, ndir, k * k},
+                                   StoreTransposedPair<NF>{c->d_bt, D::Pairs}, nplanes * D::Pairs, s)
+                 : launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
+                                   nplanes * D::Pairs, s);
     if (rc) return rc;
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
     const double L = 16.0;
@@ -286,8 +325,9 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s) {
     return PSFR_OK;
 }
 
-int run_structure_function(Ctx* c, int nplanes, cudaStream_t s) {
-    return c->NF == 1 ? structure_function_t<1>(c, nplanes, s) : structure_function_t<2>(c, nplanes, s);
+int run_structure_function(Ctx* c, int nplanes, cudaStream_t s, bool from_quadrant, int ndir) {
+    return c->NF == 1 ? structure_function_t<1>(c, nplanes, s, from_quadrant, ndir)
+                      : structure_function_t<2>(c, nplanes, s, from_quadrant, ndir);
 }
 
 template <int NF>

@@ -145,12 +145,41 @@ __global__ void psd_fill_kernel(const double* __restrict__ draws, const double* 
     }
 }
 
-int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s) {
+// one mirror quadrant of the fitting PSD, unscaled: Q[a][b], a, b < N/2 (the fit is symmetric under
+// a -> N-1-a and b -> N-1-b and identical for the directions of a draw).  The fused path never
+// materialises the N x N PSD: LoadEvenRowsQuad (psfr_passes.cu) applies the AO-zone max() and the
+// nm^2 scale with the same operations in the same order as psd_fill_kernel, so both paths give
+// bit-identical structure functions.
+__global__ void psd_quad_kernel(const double* __restrict__ draws, double* __restrict__ q, int kN) {
+    const int kNH = kN / 2;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    const int draw = blockIdx.z;
+    if (b >= kNH) return;
+    const double* dr = draws + (size_t)draw * PSFR_DRAW_NPAR;
+    const double L = 16.0, fc = 1 / (2 * (8.0 / 24.0));
+    const double L0 = dr[PSFR_DRAW_L0];
+    const double ua = (a - (kN - 1) / 2.0) / L, ub = (b - (kN - 1) / 2.0) / L;
+    const double f = sqrt(ua * ua + ub * ub);
+    double fit = 0.0;
+    if (f >= fc) fit = dr[PSFR_DRAW_FITC] * pow_m11_6(f * f + (1 / L0) * (1 / L0));
+    q[((size_t)draw * kNH + a) * kNH + b] = fit;
+}
+
+int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s, bool full) {
     const int nplanes = ndraw * ndir;
     PsdParams p{c->d_draws, c->d_geom, c->d_misc + kMiscDirs, c->d_misc + kMiscPos, c->d_ao, ndraw, ndir, ngs};
     dim3 g1((kAO * kAO + 127) / 128, nplanes);
     ao_zone_kernel<<<g1, 128, 0, s>>>(p);
     PSFR_LAUNCH_CHECK(c);
+    if (!full) {
+        dim3 gq((c->NH + 127) / 128, c->NH, ndraw);          // one quadrant per DRAW
+        psd_quad_kernel<<<gq, 128, 0, s>>>(c->d_draws, c->d_psdq, c->N);
+        PSFR_LAUNCH_CHECK(c);
+        c->planes_loaded = 0;
+        c->planes_struct = 0;
+        return PSFR_OK;
+    }
     const double k = 0.5 * 1000 / (2 * 3.141592653589793);
     dim3 g2((c->NH + 127) / 128, c->NH, nplanes);
     psd_fill_kernel<<<g2, 128, 0, s>>>(c->d_draws, c->d_ao, c->d_psd, ndir, k * k, c->N);

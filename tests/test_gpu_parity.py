@@ -375,6 +375,21 @@ def test_batch_is_independent_of_chunking(psfrec):
 
 
 # ---------------------------------------------------------------- mean + refit, polynomials (a12, a13)
+def test_fused_path_equals_staged_calls(psfrec):
+    """psfr_compute_batch (quadrant PSD, never materialised) is bit-identical to the reference-
+    shaped stage calls simul_psd_wfm -> psf_muse -> convolve_final_psf -> fit_psf_cube, which go
+    through the full N x N PSD on the host."""
+    lam = LBDA35[::11]
+    for npsflin, three in ((1, False), (2, True)):
+        seeing, GL, L0, h = 1.3, 0.55, 16., (120., 9000.)
+        tab, cube = psfrec.compute_psf(lam, seeing, GL, L0, npsflin=npsflin, h=h, three_lgs_mode=three, verbose=False)
+        psd = psfrec.simul_psd_wfm([GL, 1 - GL], h, seeing, L0, npsflin=npsflin, three_lgs_mode=three, verbose=False)
+        staged = psfrec.convolve_final_psf(lam, seeing, GL, L0, psfrec.psf_muse(psd, lam))
+        assert np.array_equal(staged, cube)
+        fit = psfrec.fit_psf_cube(lam, staged)
+        assert np.array_equal(fit['fwhm'], tab['fwhm']) and np.array_equal(fit['n'], tab['n'])
+
+
 def test_single_draw_single_wavelength(psfrec):
     """Smallest possible call: one draw, one wavelength (every ring / counter path with one item)."""
     lam = np.array([653.])
