@@ -7,6 +7,7 @@
 #pragma once
 #include "psfr_internal.h"
 #include "warp_fft.cuh"
+#include "tma.cuh"
 
 namespace psfr {
 
@@ -73,6 +74,76 @@ pass_kernel(Loader ld, Storer st, int nfft, const double2* __restrict__ g_tw, co
         st(f, lane, xb);
         __syncwarp();
     }
+}
+
+// Tile-staged variant (dim 1280): the input of a line is one contiguous block of global memory
+// (`src.block(f, &bytes)`); every warp owns a private shared-memory tile that a TMA bulk copy
+// fills while the warp transforms the previous line - the tile is dead as soon as `build` has
+// turned it into the 40 register values - so the pass streams its input at HBM speed instead of
+// waiting on dependent per-lane loads.  Lines are dealt to the warps in a fixed stride.
+template <int WARPS, int TILE_BYTES>
+constexpr size_t tiled_pass_smem() {
+    return 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) + (size_t)WARPS * (TILE_BYTES + 2 * G::XBUF * sizeof(double));
+}
+
+template <int WARPS, int TILE_BYTES, class Src, class Storer>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+tiled_pass_kernel(Src src, Storer st, int nfft, const double2* __restrict__ g_tw) {
+    static_assert(TILE_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
+    double2* tw2 = tw1 + G::TW1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(tw2 + G::TW2);
+    unsigned char* tile = tiles + (size_t)warp * TILE_BYTES;
+    double* xb = reinterpret_cast<double*>(tiles + (size_t)WARPS * TILE_BYTES) + (size_t)warp * 2 * G::XBUF;
+    uint64_t* bar = bars + warp;
+    for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+    auto fetch = [&](int f) {
+        if (lane == 0) {
+            uint32_t bytes;
+            const void* g = src.block(f, &bytes);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(tile, g, bytes, bar);
+        }
+    };
+    if (gw < nfft) fetch(gw);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int f = gw; f < nfft; f += nw) {
+        double2 v[40];
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        src.build(f, lane, tile, v);
+        __syncwarp();
+        if (f + nw < nfft) fetch(f + nw);
+        warp_fft<kR3>(v, xb + G::XBUF, tw1, tw2, lane);
+        __syncwarp();
+        fft_dump<kR3>(v, xb, lane, 0);
+        fft_dump<kR3>(v, xb + G::XBUF, lane, 1);
+        __syncwarp();
+        st(f, lane, xb);
+        __syncwarp();
+    }
+}
+
+template <int WARPS, int TILE_BYTES, class Src, class Storer>
+static int launch_tiled_pass(Ctx* c, Src src, Storer st, int nfft, cudaStream_t s) {
+    constexpr size_t smem = tiled_pass_smem<WARPS, TILE_BYTES>();
+    static_assert(smem <= 232448, "tiled pass shared memory exceeds the 227 KB per-CTA limit");
+    if (int rc = ensure_dynamic_smem(c, tiled_pass_kernel<WARPS, TILE_BYTES, Src, Storer>, smem)) return rc;
+    int grid = (nfft + WARPS - 1) / WARPS;
+    if (grid > c->sm_count) grid = c->sm_count;
+    tiled_pass_kernel<WARPS, TILE_BYTES, Src, Storer><<<grid, WARPS * 32, smem, s>>>(src, st, nfft, c->d_tw);
+    PSFR_LAUNCH_CHECK(c);
+    return PSFR_OK;
 }
 
 template <int NF, class Loader, class Storer>

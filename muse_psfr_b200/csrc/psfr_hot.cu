@@ -17,6 +17,7 @@
 //    commutes with the linear transform), keeping the 80 sampled outputs -> 80x80 samples.
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
+#include "tma.cuh"
 
 #ifndef PSFR_HOT_BLK
 #define PSFR_HOT_BLK 4
@@ -36,40 +37,6 @@ struct HotCfg {
                                    (size_t)Stages * 2 * TileBytes + (size_t)Warps * G::XBUF * sizeof(double);
     static_assert(Smem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
 
 int hot_event(Ctx* c, int which, cudaStream_t s);   // psfr_api.cu: CUDA-event bracket of the row kernel
 

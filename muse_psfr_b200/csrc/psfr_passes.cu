@@ -75,6 +75,80 @@ struct LoadEvenRowsQuad {
     }
 };
 
+// Tile sources of the tile-staged stage-A passes (dim 1280, see tiled_pass_kernel).
+// Rows: E[a][n] = (P[a][n] + P[N-a][N-n]) / 2 only touches the quadrant rows a-1, a, a+1 for the
+// pair (a, a+1) = (2rp, 2rp+1): min(a, N-1-a) of rows a, a+1, N-a, N-1-a.  One contiguous block.
+struct SrcEvenRowsQuad {
+    using D = Dim<1>;
+    static constexpr int kTileRows = 3;
+    static constexpr int kTileBytes = kTileRows * D::NH * sizeof(double);
+    const double* Q;    // [ndraw][N/2][N/2]
+    const double* ao;   // [nplanes][80][80]
+    int ndir;
+    double scale2;
+    __device__ static int first_row(int rp) { return max(2 * rp - 1, 0); }
+    __device__ const void* block(int f, uint32_t* bytes) const {
+        const int plane = f / D::Pairs, rp = f % D::Pairs;
+        const int r0 = first_row(rp), r1 = min(2 * rp + 1, D::NH - 1);
+        *bytes = (uint32_t)((r1 - r0 + 1) * D::NH * sizeof(double));
+        return Q + ((size_t)(plane / ndir) * D::NH + r0) * D::NH;
+    }
+    __device__ __forceinline__ double psd(const double* q, const double* z, int r0, int a, int n) const {
+        const int qa = a < D::NH ? a : D::N - 1 - a, qn = n < D::NH ? n : D::N - 1 - n;
+        double val = q[(qa - r0) * D::NH + qn];
+        constexpr int lo = D::NH - kAO / 2, hi = D::NH + kAO / 2;
+        if (a >= lo && a < hi && n >= lo && n < hi) val = fmax(val, __ldg(z + (a - lo) * kAO + (n - lo)));
+        return __dmul_rn(val, scale2);
+    }
+    __device__ void build(int f, int lane, const unsigned char* tile, double2* v) const {
+        const int plane = f / D::Pairs, rp = f % D::Pairs;
+        const int a1 = 2 * rp, a2 = a1 + 1, r0 = first_row(rp);
+        const double* q = reinterpret_cast<const double*>(tile);
+        const double* z = ao + (size_t)plane * kAO * kAO;
+        const int a1m = (D::N - a1) % D::N;
+        const bool ok2 = a2 <= D::NH;
+        const int a2m = ok2 ? D::N - a2 : a1;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            const int nm = (D::N - n) % D::N;
+            const double e1 = 0.5 * (psd(q, z, r0, a1, n) + psd(q, z, r0, a1m, nm));
+            const double e2 = ok2 ? 0.5 * (psd(q, z, r0, a2, n) + psd(q, z, r0, a2m, nm)) : 0.0;
+            v[i] = make_double2(e1, e2);
+        }
+    }
+};
+
+// Columns: the Hermitian pair of line (plane, m) reads the two adjacent rows y1 = (2m + N/2) % N,
+// y1 + 1 of the transposed row-pass output (the partner of the last valid row is a duplicate).
+struct SrcHermitianPair {
+    using D = Dim<1>;
+    static constexpr int kTileBytes = 2 * D::Rows * sizeof(double2);
+    const double2* Bt;  // [nplanes][N][Rows]
+    int npair, last_valid;
+    __device__ const void* block(int f, uint32_t* bytes) const {
+        const int plane = f / npair, m = f % npair;
+        *bytes = kTileBytes;
+        return Bt + ((size_t)plane * D::N + (2 * m + D::NH) % D::N) * D::Rows;
+    }
+    __device__ void build(int f, int lane, const unsigned char* tile, double2* v) const {
+        const int m = f % npair;
+        const double2* c1 = reinterpret_cast<const double2*>(tile);
+        const double2* c2 = (2 * m + 1 <= last_valid) ? c1 + D::Rows : c1;
+#pragma unroll
+        for (int i = 0; i < 40; ++i) {
+            const int n = slot_n(i, lane);
+            if (n <= D::NH) {
+                const double2 r1 = c1[n], r2 = c2[n];
+                v[i] = make_double2(r1.x - r2.y, r1.y + r2.x);
+            } else {
+                const double2 r1 = c1[D::N - n], r2 = c2[D::N - n];
+                v[i] = make_double2(r1.x + r2.y, r2.x - r1.y);
+            }
+        }
+    }
+};
+
 // rows (2f, 2f+1) of exp(-c D) * OTF on the transposed half-plane (psfrec.py:793-797)
 template <int NF>
 struct LoadOtfRows {
@@ -303,11 +377,22 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_q
     using D = Dim<NF>;
     // pass 1: rows of the even part of the PSD -> transposed half spectrum
     const double k = 0.5 * 1000 / (2 * 3.141592653589793);      // rad^2 -> nm^2 (psfrec.py:151), as run_psd
-    int rc = from_quadrant
+    int rc;
+    if constexpr (NF == 1) {
+        if (from_quadrant)
+            rc = launch_tiled_pass<5, SrcEvenRowsQuad::kTileBytes>(c, SrcEvenRowsQuad{c->d_psdq, c->d_ao, ndir, k * k},
+                                                                   StoreTransposedPair<1>{c->d_bt, D::Pairs},
+                                                                   nplanes * D::Pairs, s);
+        else
+            rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
+                                 nplanes * D::Pairs, s);
+    } else {
+        rc = from_quadrant
                  ? launch_pass<NF>(c, LoadEvenRowsQuad<NF>{c->d_psdq, c->d_ao, ndir, k * k},
                                    StoreTransposedPair<NF>{c->d_bt, D::Pairs}, nplanes * D::Pairs, s)
                  : launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
                                    nplanes * D::Pairs, s);
+    }
     if (rc) return rc;
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
     const double L = 16.0;
@@ -319,7 +404,12 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_q
     rc = launch_pass<NF>(c, LoadStrided<LoadHermitianPair<NF>>{cols, D::Pairs, D::NH / 2},
                          StoreCentre<NF>{centre, scale}, nplanes, s);
     if (rc) return rc;
-    rc = launch_pass<NF>(c, cols, StoreDphi<NF>{c->d_dphi, centre, c->d_dmin, scale}, nplanes * D::Pairs, s);
+    if constexpr (NF == 1)
+        rc = launch_tiled_pass<5, SrcHermitianPair::kTileBytes>(c, SrcHermitianPair{c->d_bt, D::Pairs, D::NH},
+                                                                StoreDphi<1>{c->d_dphi, centre, c->d_dmin, scale},
+                                                                nplanes * D::Pairs, s);
+    else
+        rc = launch_pass<NF>(c, cols, StoreDphi<NF>{c->d_dphi, centre, c->d_dmin, scale}, nplanes * D::Pairs, s);
     if (rc) return rc;
     c->planes_struct = nplanes;
     return PSFR_OK;
