@@ -138,7 +138,10 @@ __device__ __forceinline__ void accumulate_pixel(double dp, double dq, double pi
 }
 
 // accumulate normal equations at x over this lane's pixels (two independent pixel chains per
-// trip so that the log / exp latencies overlap), then reduce over the warp
+// trip so that the log / exp latencies overlap), then reduce over the warp.  STEP = 1 visits every
+// pixel; STEP = 4 every fourth pixel of each lane (a quasi-uniform quarter of the image), used
+// by the coarse first stage of the fit.
+template <int STEP>
 __device__ __forceinline__ void accumulate(const double* __restrict__ img, int npx, int nx, const double* x,
                                            double* sums) {
 #pragma unroll
@@ -147,7 +150,7 @@ __device__ __forceinline__ void accumulate(const double* __restrict__ img, int n
     const double ia2 = 1.0 / (a * a), ia = 1.0 / a;
     const int lane = threadIdx.x & 31;
     int pr = lane / nx, qc = lane % nx;          // once per call; then stepped incrementally
-    const int dpr = 32 / nx, dqc = 32 % nx;
+    const int dpr = (32 * STEP) / nx, dqc = (32 * STEP) % nx;
     auto step = [&]() {
         pr += dpr;
         qc += dqc;
@@ -157,13 +160,13 @@ __device__ __forceinline__ void accumulate(const double* __restrict__ img, int n
         }
     };
     int idx = lane;
-    for (; idx + 32 < npx; idx += 64) {
+    for (; idx + 32 * STEP < npx; idx += 64 * STEP) {
         const double dp0 = (double)pr - y0, dq0 = (double)qc - x0;
         step();
         const double dp1 = (double)pr - y0, dq1 = (double)qc - x0;
         step();
         accumulate_pixel(dp0, dq0, img[idx], I, n, ia2, ia, sums);
-        accumulate_pixel(dp1, dq1, img[idx + 32], I, n, ia2, ia, sums);
+        accumulate_pixel(dp1, dq1, img[idx + 32 * STEP], I, n, ia2, ia, sums);
     }
     if (idx < npx) accumulate_pixel((double)pr - y0, (double)qc - x0, img[idx], I, n, ia2, ia, sums);
     warp_sum_vec(sums);
@@ -207,6 +210,77 @@ __device__ __forceinline__ void chol_solve(const double (&L)[kNP][kNP], double* 
 #pragma unroll
         for (int q = i + 1; q < kNP; ++q) t = fma(-L[q][i], z[q], t);
         z[i] = t * L[i][i];
+    }
+}
+
+// Levenberg-Marquardt on the pixel subset STEP from the start point x (updated in place);
+// sums holds the normal equations at the final x.  tol2 = square of the relative step at which
+// to stop (MINPACK, the reference's solver, stops at 1.49e-8; the final stage uses 1e-9).
+template <int STEP>
+__device__ __forceinline__ void lm_solve(const double* __restrict__ img, int npx, int nx, double* x, double* sums,
+                                         double tol2, int max_iter, int& iter, int& status) {
+    double trial[kNSUM], xt[kNP], d[kNP];
+    accumulate<STEP>(img, npx, nx, x, sums);
+    double mu = 1e-3, nu = 2.0;
+    status = -1;
+    constexpr int dia[kNP] = {pk(0, 0), pk(1, 1), pk(2, 2), pk(3, 3), pk(4, 4)};
+    double L[kNP][kNP];
+    for (iter = 1; iter <= max_iter; ++iter) {
+        // every lane runs the identical solve on bit-identical sums
+        if (!cholesky(sums, mu, L)) {
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e15) break;
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < kNP; ++i) d[i] = -sums[15 + i];
+        chol_solve(L, d);
+        double dn = 0.0, xn = 0.0, pred = 0.0;
+#pragma unroll
+        for (int i = 0; i < kNP; ++i) {
+            xt[i] = x[i] + d[i];
+            const double sc2 = sums[dia[i]];                  // |J column|^2
+            dn = fma(d[i] * d[i], sc2, dn);
+            xn = fma(x[i] * x[i], sc2, xn);
+            // predicted decrease of r.r : d.(mu D d - g)
+            pred += d[i] * (mu * sc2 * d[i] - sums[15 + i]);
+        }
+        if (!(xt[3] > 0.0) || !(xt[4] > 0.0) || !isfinite(xt[0])) {
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e15) break;
+            continue;
+        }
+        accumulate<STEP>(img, npx, nx, xt, trial);
+        const double actual = sums[20] - trial[20];
+        // near the minimum the cost is flat to rounding: tolerate a noise-level increase so that
+        // Gauss-Newton steps keep contracting, and stop on the (column-scaled) step size
+        // MINPACK (the reference, through mpdaf -> scipy leastsq) stops at a relative step of 1.49e-8
+        const bool small = dn <= tol2 * (xn + 1e-300);            // relative step <= sqrt(tol2)
+        if (isfinite(trial[20]) && actual >= -1e-13 * sums[20]) {
+            const double rho = pred > 0.0 ? actual / pred : 1.0;
+#pragma unroll
+            for (int i = 0; i < kNP; ++i) x[i] = xt[i];
+#pragma unroll
+            for (int k = 0; k < kNSUM; ++k) sums[k] = trial[k];
+            const double t = 2.0 * rho - 1.0;
+            mu *= fmax(1.0 / 3.0, 1.0 - t * t * t);
+            if (mu < 1e-15) mu = 1e-15;
+            nu = 2.0;
+            if (small) {
+                status = iter;
+                break;
+            }
+        } else {
+            if (dn <= 1e-18 * (xn + 1e-300)) {   // step below 1e-9 relative and no decrease: rounding floor
+                status = iter;
+                break;
+            }
+            mu *= nu;
+            nu *= 2.0;
+            if (mu > 1e15) break;
+        }
     }
 }
 
@@ -263,7 +337,7 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         num += __shfl_xor_sync(0xffffffffu, num, o);
         den += __shfl_xor_sync(0xffffffffu, den, o);
     }
-    double x[kNP], sums[kNSUM], trial[kNSUM], xt[kNP], d[kNP];
+    double x[kNP], sums[kNSUM];
     {
         const double wp = sqrt(num / den);
         const double fwhm0 = wp * 2.0 * sqrt(2.0 * log(2.0));
@@ -273,69 +347,16 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         x[3] = fwhm0 / (2.0 * sqrt(sqrt(2.0) - 1.0));
         x[4] = 2.0;
     }
-    accumulate(img, npx, nx, x, sums);
-    double mu = 1e-3, nu = 2.0;
+    // Stage 1: Levenberg-Marquardt on a quarter of the pixels down to a relative step of 1e-3 - it
+    // only moves the start point (the converged minimum does not depend on it); stage 2: all
+    // pixels down to 1e-9.
     int iter = 0, status = -1;
-    const int max_iter = 200;
-    constexpr int dia[kNP] = {pk(0, 0), pk(1, 1), pk(2, 2), pk(3, 3), pk(4, 4)};
-    double L[kNP][kNP];
-    for (iter = 1; iter <= max_iter; ++iter) {
-        // every lane runs the identical solve on bit-identical sums
-        if (!cholesky(sums, mu, L)) {
-            mu *= nu;
-            nu *= 2.0;
-            if (mu > 1e15) break;
-            continue;
-        }
-#pragma unroll
-        for (int i = 0; i < kNP; ++i) d[i] = -sums[15 + i];
-        chol_solve(L, d);
-        double dn = 0.0, xn = 0.0, pred = 0.0;
-#pragma unroll
-        for (int i = 0; i < kNP; ++i) {
-            xt[i] = x[i] + d[i];
-            const double sc2 = sums[dia[i]];                  // |J column|^2
-            dn = fma(d[i] * d[i], sc2, dn);
-            xn = fma(x[i] * x[i], sc2, xn);
-            // predicted decrease of r.r : d.(mu D d - g)
-            pred += d[i] * (mu * sc2 * d[i] - sums[15 + i]);
-        }
-        if (!(xt[3] > 0.0) || !(xt[4] > 0.0) || !isfinite(xt[0])) {
-            mu *= nu;
-            nu *= 2.0;
-            if (mu > 1e15) break;
-            continue;
-        }
-        accumulate(img, npx, nx, xt, trial);
-        const double actual = sums[20] - trial[20];
-        // near the minimum the cost is flat to rounding: tolerate a noise-level increase so that
-        // Gauss-Newton steps keep contracting, and stop on the (column-scaled) step size
-        // MINPACK (the reference, through mpdaf -> scipy leastsq) stops at a relative step of 1.49e-8
-        const bool small = dn <= 1e-18 * (xn + 1e-300);            // relative step <= 1e-9
-        if (isfinite(trial[20]) && actual >= -1e-13 * sums[20]) {
-            const double rho = pred > 0.0 ? actual / pred : 1.0;
-#pragma unroll
-            for (int i = 0; i < kNP; ++i) x[i] = xt[i];
-#pragma unroll
-            for (int k = 0; k < kNSUM; ++k) sums[k] = trial[k];
-            const double t = 2.0 * rho - 1.0;
-            mu *= fmax(1.0 / 3.0, 1.0 - t * t * t);
-            if (mu < 1e-15) mu = 1e-15;
-            nu = 2.0;
-            if (small) {
-                status = iter;
-                break;
-            }
-        } else {
-            if (dn <= 1e-18 * (xn + 1e-300)) {   // step below 1e-9 relative and no decrease: rounding floor
-                status = iter;
-                break;
-            }
-            mu *= nu;
-            nu *= 2.0;
-            if (mu > 1e15) break;
-        }
-    }
+    lm_solve<4>(img, npx, nx, x, sums, 1e-6, 12, iter, status);
+    const int coarse_iter = iter;
+    lm_solve<1>(img, npx, nx, x, sums, 1e-18, 200, iter, status);
+    iter += coarse_iter;
+    if (status > 0) status += coarse_iter;
+    const int max_iter = 212;
     if (lane == 0) {
         double* o = out + (size_t)image * PSFR_FIT_NPAR;
         const double a = fabs(x[3]), n = x[4];
@@ -349,6 +370,7 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         o[PSFR_FIT_CHISQ] = sums[20];
         o[PSFR_FIT_ITER] = (status > 0) ? (double)status : -(double)(iter > max_iter ? max_iter : iter);
         const double dof = (double)(npx - kNP);
+        double L[kNP][kNP];
         if (cholesky(sums, 0.0, L)) {
             double e[kNP];
 #pragma unroll
@@ -498,7 +520,13 @@ int run_fit(Ctx* c, int nimg, int ny, int nx, const double* img_dev, double* fit
     if (smem > 200 * 1024) return set_error(c, PSFR_E_UNSUPPORTED, "image %dx%d too large for the fitter", ny, nx);
     if (int rc = ensure_dynamic_smem(c, fit_kernel, smem)) return rc;
     int grid = (nimg + kFitWarps - 1) / kFitWarps;
-    const int resident = c->sm_count * 3;            // 166 registers x 128 threads: three CTAs per SM
+    int per_sm = 2;                                  // persistent grid: as many CTAs as are resident at once
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel, kFitWarps * 32, smem) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    const int resident = c->sm_count * per_sm;
     if (grid > resident) grid = resident;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter + 1, 0, sizeof(int), s));
     fit_kernel<<<grid, kFitWarps * 32, smem, s>>>(img_dev, nimg, ny, nx, fit_dev, c->d_counter + 1);
