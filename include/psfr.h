@@ -160,8 +160,18 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  * row pairs that are below the cut everywhere are not transformed.  The OTF peak is 1, so
  * the default drops terms below 1.6e-28 of it - twelve orders of magnitude under the FP64
  * rounding of the transform itself.  A value >= 745 (exp underflows) disables the cut.
- * psfr_psd_to_psf (full-grid parity mode) never applies it. */
-enum { PSFR_OPT_EXP_CUT = 1 };
+ * psfr_psd_to_psf (full-grid parity mode) never applies it (nor the grades below).
+ *
+ * Graded precision of the same pass (the OTF peak is exactly 1, so an entry's size bounds
+ * what an error in it can do to the result):
+ * PSFR_OPT_EXP_GRADE (default 25): a block of 2 x 160 OTF entries whose every live entry is
+ * below exp(-grade) = 1.4e-11 evaluates exp on the special-function unit in single precision
+ * (relative error ~4e-6, i.e. < 1e-16 of the peak per entry); other blocks use the FP64 exp.
+ * PSFR_OPT_F32_ROWS (default 30, dim 1280 only): a row pair whose every entry is below
+ * exp(-thr) = 9.4e-14 is evaluated AND transformed in single precision (error < 1e-19 of the
+ * peak per output); all other rows and the whole column pass are FP64.
+ * A threshold >= the cut disables the respective grade (e.g. 1e30). */
+enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3 };
 PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
 
 /* Introspection used by tests and the bench --------------------------------------- */

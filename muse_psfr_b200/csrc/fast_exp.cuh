@@ -39,6 +39,23 @@ __device__ __forceinline__ double fast_exp(double x) {
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// 2^x on the special-function unit (MUFU.EX2), relative error 2^-22; flushes to zero below 2^-126.
+// Used only where the result is below exp(-25) of the OTF peak (psfr_hot.cu).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// float -> double on the integer pipe (F2F issues at a quarter of the DFMA rate): exact for
+// normal non-negative floats; +0 and denormals map to values below 2^-126, which is as good as
+// zero for an OTF entry.  The sign bit must be clear (-0.0f would come out as 2^129): the
+// operands are exp(...) >= 0 and the telescope OTF, which finalize_otf_kernel keeps at >= +0.
+__device__ __forceinline__ double f2d_bits(float f) {
+    const unsigned b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
 // sign-agnostic test for zero and "x <= -cut" on the integer pipe.  For x < 0 the high word
 // grows with |x|, so x <= -cut <=> hi(x) >= hi(-cut) as unsigned (up to the low word of cut,
 // which is irrelevant for a threshold); non-negative x has the sign bit clear and never passes.

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 #include "psfr_internal.h"
+#include <algorithm>
 #include "warp_fft.cuh"
 #include "fft_tables.h"
 
@@ -88,6 +89,7 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_frac, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kidx, kx.data(), kx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));   // the host vectors go out of scope
+    c->clam_min = *std::min_element(cl.begin(), cl.end());
     return PSFR_OK;
 }
 
@@ -167,6 +169,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
+    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -242,6 +245,11 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_bt, P * kN * kRows));
     CK(dev_alloc(c, &c->d_dphi, P * kRows * kN));
     CK(dev_alloc(c, &c->d_dmin, P * kRows));
+    if (c->NF == 1) {
+        CK(dev_alloc(c, &c->d_dphi32, P * kRows * kN));
+        CK(dev_alloc(c, &c->d_otf32, (size_t)kRows * kN));
+        CK(dev_alloc(c, &c->d_tw32, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
+    }
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNS * kRows));
     CK(dev_alloc(c, &c->d_samp, P * LM * kNS * kNS));
@@ -275,6 +283,12 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     build_twiddles<kR3>(tw1, tw2);
     CKC(cudaMemcpy(c->d_tw, tw1.data(), tw1.size() * sizeof(double2), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_tw + tw1.size(), tw2.data(), tw2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    if (c->d_tw32) {
+        std::vector<float2> tw32(tw1.size() + tw2.size());
+        for (size_t i = 0; i < tw1.size(); ++i) tw32[i] = make_float2((float)tw1[i].x, (float)tw1[i].y);
+        for (size_t i = 0; i < tw2.size(); ++i) tw32[tw1.size() + i] = make_float2((float)tw2[i].x, (float)tw2[i].y);
+        CKC(cudaMemcpy(c->d_tw32, tw32.data(), tw32.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     {
         std::vector<double2> twc(kNB);
         for (int k = 0; k < kNB; ++k) twc[k] = unit_root(k, c->N);
@@ -608,6 +622,14 @@ int psfr_set_option(psfr_ctx* c, int key, double value) {
         case PSFR_OPT_EXP_CUT:
             if (!(value > 0)) return set_error(c, PSFR_E_ARG, "exp cut must be positive (got %g)", value);
             c->exp_cut = value;
+            return PSFR_OK;
+        case PSFR_OPT_EXP_GRADE:
+            if (!(value > 0)) return set_error(c, PSFR_E_ARG, "exp grade must be positive (got %g)", value);
+            c->exp_grade = value;
+            return PSFR_OK;
+        case PSFR_OPT_F32_ROWS:
+            if (!(value > 0)) return set_error(c, PSFR_E_ARG, "f32 row threshold must be positive (got %g)", value);
+            c->f32_rows = value;
             return PSFR_OK;
         default:
             return set_error(c, PSFR_E_ARG, "unknown option %d", key);

@@ -25,16 +25,22 @@
 
 namespace psfr {
 
-// Launch shape per grid size: the ring stage holds two rows of D and two of the telescope OTF
-// (4 N doubles), so dim 2560 affords two stages and four transform warps in 227 KB.
+// Launch shape per grid size.  dim 1280: a ring stage holds two rows of D and of the telescope
+// OTF in double AND in single precision (6 N doubles = 60 KB); two stages, eight transform warps.
+// The single-precision copies feed the block grading and the FP32 row pairs without any
+// double -> float conversion in the kernel (F2F issues at a quarter of the DFMA rate).
+// dim 2560: FP64 only (4 N doubles = 80 KB per stage), two stages, four warps, no grading.
 template <int NF>
 struct HotCfg {
+    static constexpr bool F32 = NF == 1;             // single-precision copies staged, grading on
     static constexpr int Warps = NF == 1 ? 8 : 4;    // consumer warps
-    static constexpr int Stages = NF == 1 ? 3 : 2;   // ring depth
-    static constexpr int Tile = 2 * Dim<NF>::N;      // doubles per tile (two rows)
+    static constexpr int Stages = 2;                 // ring depth
+    static constexpr int Tile = 2 * Dim<NF>::N;      // elements per tile (two rows)
     static constexpr uint32_t TileBytes = Tile * sizeof(double);
+    static constexpr uint32_t TileBytes32 = Tile * sizeof(float);
+    static constexpr uint32_t StageBytes = 2 * TileBytes + (F32 ? 2 * TileBytes32 : 0);
     static constexpr size_t Smem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
-                                   (size_t)Stages * 2 * TileBytes + (size_t)Warps * G::XBUF * sizeof(double);
+                                   (size_t)Stages * StageBytes + (size_t)Warps * G::XBUF * sizeof(double);
     static_assert(Smem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
 };
 
@@ -47,9 +53,15 @@ struct HotParams {
     const double* clam;    // [nlam]
     const uint16_t* kidx;  // [nlam][kNS]
     const double2* wsamp;  // [nlam][2][kNS] NF = 2: w_N^k of the sampled outputs and of their mirrors
-    const double* dmin;    // [nplanes][kRows] smallest D of each row (finalize_dphi_kernel)
+    const double* dmin;    // [nplanes][kRows] smallest D of each row (StoreDphi)
+    const float* D32;      // single-precision copies of D and T (dim 1280)
+    const float* T32;
+    const float2* tw32;    // single-precision twiddles (global memory, L1-resident)
+    double cmin;           // smallest c_lambda: a row pair with cmin * min(D) > cut is dead at every wavelength
     int* next_item;        // work counter, zeroed before the launch
     double cut;            // OTF entries with c*D > cut (exp < e^-cut) are flushed to zero
+    double grade;          // blocks whose live entries all have c*D >= grade take the single-precision exp
+    double f32_min;        // row pairs with c*min(D) >= f32_min run entirely in single precision (NF = 1)
     int nplanes, nlam;
 };
 
@@ -60,15 +72,18 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     using C = HotCfg<NF>;
     constexpr int kStages = C::Stages, kHotWarps = C::Warps, kTile = C::Tile, kN = D::N, kRows = D::Rows,
                   kPairs = D::Pairs;
-    constexpr uint32_t kTileBytes = C::TileBytes;
+    constexpr uint32_t kTileBytes = C::TileBytes, kTileBytes32 = C::TileBytes32;
+    constexpr size_t kStageDoubles = C::StageBytes / sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);   // per-stage count of warps done with it
     volatile int* item_of = released + kStages;               // per-stage work item (-1: no more work)
+    volatile double* dmin_of = reinterpret_cast<volatile double*>(smem_raw + 64);   // per-stage min(D) of the row pair
+    static_assert(kStages <= 4, "the 128-byte header holds four stages");
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
-    double* ring = reinterpret_cast<double*>(tw2 + G::TW2);   // [stage][D tile | T tile]
-    double* xall = ring + (size_t)kStages * 2 * kTile;
+    double* ring = reinterpret_cast<double*>(tw2 + G::TW2);   // [stage][D | T | D32 | T32]
+    double* xall = ring + (size_t)kStages * kStageDoubles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.nplanes * kPairs;
 
@@ -81,11 +96,26 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
         const int item = atomicAdd(p.next_item, 1);
         if (item < items) {
             const int plane = item / kPairs, rp = item % kPairs;
-            double* dst = ring + (size_t)s * 2 * kTile;
+            double* dst = ring + (size_t)s * kStageDoubles;
             item_of[s] = item;
-            mbar_expect_tx(full + s, 2 * kTileBytes);
-            tma_load_1d(dst, p.D + ((size_t)plane * kRows + 2 * rp) * kN, kTileBytes, full + s);
-            tma_load_1d(dst + kTile, p.T + (size_t)(2 * rp) * kN, kTileBytes, full + s);
+            // a row pair that is below the cut at the longest wavelength is below it at all of
+            // them: the consumers only write zeros and never look at the stage
+            const double dm = fmin(__ldg(p.dmin + (size_t)plane * kRows + 2 * rp),
+                                   __ldg(p.dmin + (size_t)plane * kRows + 2 * rp + 1));
+            dmin_of[s] = dm;   // travels with the item id: the consumers need it before anything else
+            if (p.cmin * dm > p.cut) {
+                mbar_arrive(full + s);
+                return;
+            }
+            const size_t off = ((size_t)plane * kRows + 2 * rp) * kN, offT = (size_t)(2 * rp) * kN;
+            mbar_expect_tx(full + s, C::StageBytes);
+            tma_load_1d(dst, p.D + off, kTileBytes, full + s);
+            tma_load_1d(dst + kTile, p.T + offT, kTileBytes, full + s);
+            if (C::F32) {
+                float* dst32 = reinterpret_cast<float*>(dst + 2 * kTile);
+                tma_load_1d(dst32, p.D32 + off, kTileBytes32, full + s);
+                tma_load_1d(dst32 + kTile, p.T32 + offT, kTileBytes32, full + s);
+            }
         } else {
             item_of[s] = -1;
             mbar_arrive(full + s);
@@ -105,26 +135,77 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     __syncthreads();
 
     double* xb = xall + (size_t)warp * G::XBUF;
+    // Units (item, wavelength) are numbered g = seq * nlam + lam in the order in which this CTA
+    // receives its items (seq = 0, 1, ...) and dealt to the warps in ROUNDS of eight: warp w
+    // takes unit 8 R + w of round R, and all warps enter a round together (one CTA barrier).
+    // The unit body is ~70 KB of straight-line code, far more than the instruction caches
+    // hold; warps that run it side by side share every fetched line, warps that drift apart
+    // each stream it from L2 on their own (ncu: `no_instruction` was the top stall and FP32
+    // units, whose code adds 40 KB, made the kernel slower until the rounds were aligned).
+    //
+    // A warp passes through EVERY item in order - wait for its fill, release it when its next
+    // unit lies in a later item - also when it has no unit in it: that keeps all warps within
+    // kStages items of each other, which the per-stage release counter and the phase parity
+    // rely on.  Fills are issued in order, so the first -1 is followed by -1 only and no TMA
+    // is in flight when the CTA retires.
+    int cur = 0;            // sequence number of the item this warp is in
+    bool seen = false;      // its fill has been observed
+    auto enter = [&](int seq) {
+        while (true) {
+            if (!seen) {
+                mbar_wait(full + cur % kStages, (cur / kStages) & 1);
+                seen = true;
+            }
+            if (cur == seq) break;
+            // release the stage; the last warp to do so refills it with the next work item
+            __syncwarp();
+            if (lane == 0) {
+                const int s = cur % kStages;
+                __threadfence_block();
+                const int old = atomicAdd(released + s, 1);
+                if (old == kHotWarps - 1) {
+                    atomicExch(released + s, 0);
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(s);
+                }
+            }
+            __syncwarp();
+            ++cur;
+            seen = false;
+        }
+        return item_of[cur % kStages];
+    };
+    // A round must not span more items than the ring has stages (its later units would wait for
+    // a fill that needs the release of its earlier ones): with rs <= nlam units per round it
+    // spans at most two.  Warps beyond rs (only when nlam < 8) idle through the rounds.
+    const int rs = p.nlam < kHotWarps ? p.nlam : kHotWarps;
+    int seq0 = 0, lam0 = 0;   // (item, wavelength) of the round's first unit, advanced without divisions
 #pragma unroll 1
-    for (int it = 0;; ++it) {
-        const int s = it % kStages, u = it / kStages;
-        // every warp observes every fill, also when it has no wavelength in this item: that keeps
-        // all warps within kStages items of each other, which the per-stage release counter and
-        // the phase parity rely on.  Fills are issued in iteration order, so the first -1 a warp
-        // sees is followed by -1 only and no TMA is in flight when the CTA retires.
-        mbar_wait(full + s, u & 1);
-        const int item = item_of[s];
-        if (item < 0) break;
-        // flat (item, wavelength) index g = it*nlam + lam is dealt round-robin to the warps
-        int lam = (warp - (int)(((long long)it * p.nlam) % kHotWarps) + kHotWarps) % kHotWarps;
-        if (lam < p.nlam) {
-            const double* sD = ring + (size_t)s * 2 * kTile;
+    for (;;) {
+        __syncthreads();
+        // the round's first unit decides for everybody: items only get later within a round
+        if (enter(seq0) < 0) break;
+        int seq = seq0, lam = lam0 + warp;
+        if (lam >= p.nlam) {
+            lam -= p.nlam;
+            ++seq;
+        }
+        const int item = warp < rs ? enter(seq) : -1;
+        lam0 += rs;
+        if (lam0 >= p.nlam) {
+            lam0 -= p.nlam;
+            ++seq0;
+        }
+        if (item >= 0) {
+            const int s = seq % kStages;
+            const double* sD = ring + (size_t)s * kStageDoubles;
             const double* sT = sD + kTile;
+            const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);   // dim 1280 only
+            const float* sT32 = sD32 + kTile;
             const int plane = item / kPairs, rp = item % kPairs;
-            const double dm = fmin(__ldg(p.dmin + (size_t)plane * kRows + 2 * rp),
-                                   __ldg(p.dmin + (size_t)plane * kRows + 2 * rp + 1));
-#pragma unroll 1
-            for (; lam < p.nlam; lam += kHotWarps) {
+            const double dm = dmin_of[s];
+            do {   // one unit; `continue` leaves it
                 const double cl = __ldg(p.clam + lam);
                 double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
                 if (cl * dm > p.cut) {
@@ -141,44 +222,131 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     continue;
                 }
                 const double negc = -cl;
-                const unsigned cut_hi = (unsigned)__double2hiint(-p.cut);
                 // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
                 const uint16_t* kx = p.kidx + (size_t)lam * kNS;
                 int ka[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
                 double2 za[3], zb[3];   // X[kA], X[kB] accumulated over the NF interleaved sub-sequences
-#pragma unroll 1
-                for (int sub = 0; sub < NF; ++sub) {
-                    double2 v[40];
-                    // kBlk slots (= 2 kBlk independent exp chains) per basic block
-                    constexpr int kBlk = PSFR_HOT_BLK;
+                // Cut and grade thresholds on D itself, tested on the integer pipe: a non-negative
+                // float (double) orders like its bit pattern (high word); the SIGNED compare keeps a
+                // D rounded slightly below zero alive.
+                const float negc2f = (float)(negc * 1.44269504088896338700);   // exp(-c D) = 2^(negc2f D)
+                const int cut32 = __float_as_int((float)(p.cut / cl));
+                const int grade32 = __float_as_int((float)(p.grade / cl));
+                if (C::F32 && cl * dm >= p.f32_min) {
+                    // ---- single-precision unit: every entry of both rows is below exp(-f32_min)
+                    // (default e^-30 = 9.4e-14) of the OTF peak, so a relative error of 1e-6 in this
+                    // unit's contribution is < 1e-19 of the peak: exp (MUFU ex2), the products and
+                    // the transform run in FP32, off the FP64 pipe, from the FP32 copies of D and T.
+                    float2 vf[40];
 #pragma unroll
-                    for (int i = 0; i < 40; i += kBlk) {
-                        double tt[2 * kBlk], xx[2 * kBlk];
+                    for (int n1 = 0; n1 < 8; ++n1) {
+                        float df[10], tf[10];
                         bool dead = true;
 #pragma unroll
-                        for (int q = 0; q < kBlk; ++q) {
-                            const int n = slot_e<NF>(i + q, lane, sub);
-                            tt[2 * q] = sT[n];
-                            tt[2 * q + 1] = sT[kN + n];
-                            xx[2 * q] = negc * sD[n];
-                            xx[2 * q + 1] = negc * sD[kN + n];
-                            // outside the pupil-autocorrelation support the OTF is exactly zero;
-                            // below the underflow cut it is flushed to zero
-                            dead = dead & (is_zero_bits(tt[2 * q]) | below_cut(xx[2 * q], cut_hi)) &
-                                   (is_zero_bits(tt[2 * q + 1]) | below_cut(xx[2 * q + 1], cut_hi));
+                        for (int j = 0; j < 5; ++j) {
+                            const int n = slot_e<NF>(j * 8 + n1, lane, 0);
+                            df[2 * j] = sD32[n];
+                            df[2 * j + 1] = sD32[kN + n];
+                            tf[2 * j] = sT32[n];
+                            tf[2 * j + 1] = sT32[kN + n];
+                            dead = dead & ((tf[2 * j] == 0.f) | (__float_as_int(df[2 * j]) >= cut32)) &
+                                   ((tf[2 * j + 1] == 0.f) | (__float_as_int(df[2 * j + 1]) >= cut32));
                         }
                         if (__all_sync(0xffffffffu, dead)) {
 #pragma unroll
-                            for (int q = 0; q < kBlk; ++q) v[i + q] = make_double2(0.0, 0.0);
+                            for (int j = 0; j < 5; ++j) vf[j * 8 + n1] = make_float2(0.f, 0.f);
                         } else {
-                            double ee[2 * kBlk];
 #pragma unroll
-                            for (int q = 0; q < 2 * kBlk; ++q) ee[q] = fast_exp(xx[q]);
+                            for (int j = 0; j < 5; ++j)
+                                vf[j * 8 + n1] = make_float2(ex2_approx(negc2f * df[2 * j]) * tf[2 * j],
+                                                             ex2_approx(negc2f * df[2 * j + 1]) * tf[2 * j + 1]);
+                        }
+                    }
+                    warp_fft<kR3>(vf, xb, p.tw32, p.tw32 + G::TW1, lane);
+                    float2* xf = reinterpret_cast<float2*>(xb);
+                    fft_dump<kR3>(vf, xf, lane, 0);
+                    __syncwarp();
 #pragma unroll
-                            for (int q = 0; q < kBlk; ++q)
-                                v[i + q] = make_double2(ee[2 * q] * tt[2 * q], ee[2 * q + 1] * tt[2 * q + 1]);
+                    for (int i = 0; i < 3; ++i) {
+                        const float2 a = xf[nat_addr(ka[i] % kNB)];
+                        const float2 b = xf[nat_addr(((kN - ka[i]) % kN) % kNB)];
+                        za[i] = make_double2((double)a.x, (double)a.y);
+                        zb[i] = make_double2((double)b.x, (double)b.y);
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll 1
+                for (int sub = 0; sub < NF; ++sub) {
+                    double2 v[40];
+                    // One block = the 160 contiguous cells n1*160 .. n1*160+159 of both rows (slots
+                    // j*8 + n1, j = 0..4): ten independent exp chains per lane.  Three grades,
+                    // chosen per block by a warp vote on the FP32 copies: dead (outside the pupil-
+                    // autocorrelation support, where the OTF is exactly zero, or below the underflow
+                    // cut) -> zeros; every live entry below exp(-grade) (default e^-25 = 1.4e-11 of
+                    // the peak) -> MUFU ex2 and the product in single precision, absolute error
+                    // < 1e-16 of the peak; else FP64 values from the ring and the full FP64 exp.
+#pragma unroll
+                    for (int n1 = 0; n1 < 8; ++n1) {
+                        bool dead = true, cheap = true;
+                        float df[10], tf[10];
+                        double dd[10], tt[10];
+                        if (C::F32) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                const int n = slot_e<NF>(j * 8 + n1, lane, sub);
+                                df[2 * j] = sD32[n];
+                                df[2 * j + 1] = sD32[kN + n];
+                                tf[2 * j] = sT32[n];
+                                tf[2 * j + 1] = sT32[kN + n];
+#pragma unroll
+                                for (int r = 0; r < 2; ++r) {
+                                    const bool z = tf[2 * j + r] == 0.f;
+                                    const int h = __float_as_int(df[2 * j + r]);
+                                    dead = dead & (z | (h >= cut32));
+                                    cheap = cheap & (z | (h >= grade32));
+                                }
+                            }
+                        } else {
+                            const int cut_hi = __double2hiint(p.cut / cl);
+                            cheap = false;
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                const int n = slot_e<NF>(j * 8 + n1, lane, sub);
+                                dd[2 * j] = sD[n];
+                                dd[2 * j + 1] = sD[kN + n];
+                                tt[2 * j] = sT[n];
+                                tt[2 * j + 1] = sT[kN + n];
+                                dead = dead & (is_zero_bits(tt[2 * j]) | (__double2hiint(dd[2 * j]) >= cut_hi)) &
+                                       (is_zero_bits(tt[2 * j + 1]) | (__double2hiint(dd[2 * j + 1]) >= cut_hi));
+                            }
+                        }
+                        if (__all_sync(0xffffffffu, dead)) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) v[j * 8 + n1] = make_double2(0.0, 0.0);
+                        } else if (C::F32 && __all_sync(0xffffffffu, cheap)) {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j)
+                                v[j * 8 + n1] = make_double2(f2d_bits(ex2_approx(negc2f * df[2 * j]) * tf[2 * j]),
+                                                             f2d_bits(ex2_approx(negc2f * df[2 * j + 1]) * tf[2 * j + 1]));
+                        } else {
+                            if (C::F32) {
+#pragma unroll
+                                for (int j = 0; j < 5; ++j) {
+                                    const int n = slot_e<NF>(j * 8 + n1, lane, sub);
+                                    dd[2 * j] = sD[n];
+                                    dd[2 * j + 1] = sD[kN + n];
+                                    tt[2 * j] = sT[n];
+                                    tt[2 * j + 1] = sT[kN + n];
+                                }
+                            }
+                            double ee[10];
+#pragma unroll
+                            for (int q = 0; q < 10; ++q) ee[q] = fast_exp(negc * dd[q]);
+#pragma unroll
+                            for (int j = 0; j < 5; ++j)
+                                v[j * 8 + n1] = make_double2(ee[2 * j] * tt[2 * j], ee[2 * j + 1] * tt[2 * j + 1]);
                         }
                     }
                     warp_fft<kR3>(v, xb, tw1, tw2, lane);
@@ -225,6 +393,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         }
                     }
                 }
+                }
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int y = lane + 32 * i;
@@ -234,20 +403,11 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         o[1] = make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x));
                     }
                 }
-            }
+            } while (false);
         }
-        // release the stage; the last warp to do so refills it with the next work item
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            const int old = atomicAdd(released + s, 1);
-            if (old == kHotWarps - 1) {
-                atomicExch(released + s, 0);
-                __threadfence_block();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(s);
-            }
-        }
+        // leave the items that lie wholly before the next round BEFORE its barrier, so that
+        // their stages can be refilled while the slower warps finish this round
+        enter(seq0);
     }
 }
 
@@ -393,8 +553,8 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     using C = HotCfg<NF>;
     if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_counter,
-                c->exp_cut, nplanes, nlam};
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_dphi32,
+                c->d_otf32, c->d_tw32, c->clam_min, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));

@@ -63,8 +63,14 @@ struct Ctx {
     double2* d_bt = nullptr;     // [max_planes][N][rows] transposed row-pass output (full mode)
     double* d_dphi = nullptr;    // [max_planes][rows][N] structure function (transposed half-plane)
     double* d_dmin = nullptr;    // [max_planes][rows] smallest structure-function value of each row
+    float* d_dphi32 = nullptr;   // [max_planes][rows][N] single-precision copy of d_dphi (dim 1280: block grading + FP32 row pairs)
+    float* d_otf32 = nullptr;    // [rows][N] single-precision copy of d_otf
+    float2* d_tw32 = nullptr;    // twiddles of d_tw rounded to single precision
+    double clam_min = 0.0;       // smallest c_lambda of the current wavelength table
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
+    double exp_grade = 25.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
+    double f32_rows = 30.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples

@@ -302,10 +302,12 @@ struct StoreDphi {
     const double* centre;   // [nplanes]
     double* dmin;           // [nplanes][Rows]
     double scale;
+    float* out32;           // single-precision copy of `out` (may be NULL)
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / D::Pairs, m = f % D::Pairs;
         const int o1 = 2 * m, o2 = o1 + 1;
         double* r1 = out + ((size_t)plane * D::Rows + o1) * D::N;
+        float* q1 = out32 ? out32 + ((size_t)plane * D::Rows + o1) * D::N : nullptr;
         const bool ok2 = o2 <= D::NH;
         const double c0 = __ldg(centre + plane);
         double m1 = 1e300, m2 = ok2 ? 1e300 : 0.0;
@@ -318,6 +320,10 @@ struct StoreDphi {
             const double d2 = ok2 ? c0 + s1 * z.y : 0.0;
             r1[b] = d1;
             r1[D::N + b] = d2;
+            if (q1) {
+                q1[b] = (float)d1;
+                q1[D::N + b] = (float)d2;
+            }
             m1 = fmin(m1, d1);
             m2 = fmin(m2, d2);
         }
@@ -365,10 +371,16 @@ __global__ void pupil_kernel(double* pup, int nh, double radius, double oc) {
 }
 
 // T = rint(autocorrelation counts) / (N^2 * sum(pupil)), pad row zero
-__global__ void finalize_otf_kernel(double* t, size_t live, size_t total, double inv_norm) {
+__global__ void finalize_otf_kernel(double* t, float* t32, size_t live, size_t total, double inv_norm) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    t[idx] = (idx >= live) ? 0.0 : rint(t[idx]) * inv_norm;
+    // counts are >= 0; a count that the transform left at -0.3 must become +0, not -0: the
+    // single-precision grade of the row kernel builds doubles from float bit patterns
+    // (f2d_bits) and relies on a clear sign bit
+    const double r = (idx >= live) ? 0.0 : rint(t[idx]);
+    const double v = r > 0.0 ? r * inv_norm : 0.0;
+    t[idx] = v;
+    if (t32) t32[idx] = (float)v;
 }
 
 // ------------------------------------------------------------------ drivers
@@ -406,10 +418,10 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_q
     if (rc) return rc;
     if constexpr (NF == 1)
         rc = launch_tiled_pass<5, SrcHermitianPair::kTileBytes>(c, SrcHermitianPair{c->d_bt, D::Pairs, D::NH},
-                                                                StoreDphi<1>{c->d_dphi, centre, c->d_dmin, scale},
+                                                                StoreDphi<1>{c->d_dphi, centre, c->d_dmin, scale, c->d_dphi32},
                                                                 nplanes * D::Pairs, s);
     else
-        rc = launch_pass<NF>(c, cols, StoreDphi<NF>{c->d_dphi, centre, c->d_dmin, scale}, nplanes * D::Pairs, s);
+        rc = launch_pass<NF>(c, cols, StoreDphi<NF>{c->d_dphi, centre, c->d_dmin, scale, c->d_dphi32}, nplanes * D::Pairs, s);
     if (rc) return rc;
     c->planes_struct = nplanes;
     return PSFR_OK;
@@ -472,7 +484,7 @@ static int build_otf_t(Ctx* c, cudaStream_t s) {
     if (!(c->pup_sum > 0)) return set_error(c, PSFR_E_CUDA, "telescope OTF init failed (pupil sum %g)", centre);
     const size_t total = (size_t)D::Rows * D::N;
     finalize_otf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        c->d_otf, (size_t)(D::NH + 1) * D::N, total, 1.0 / ((double)D::N * D::N * c->pup_sum));
+        c->d_otf, c->d_otf32, (size_t)(D::NH + 1) * D::N, total, 1.0 / ((double)D::N * D::N * c->pup_sum));
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }

@@ -25,6 +25,12 @@
 //
 // Every function is __host__ __device__ so that tools/host_check.cu can run the very
 // same code lane by lane on the CPU.
+//
+// The transform is templated on the complex type Z: double2 (the product path) or float2, which
+// the stage-B row kernel uses for row pairs whose every entry is below exp(-30) of the OTF peak
+// (psfr_hot.cu).  A float2 is one 8-byte shared-memory word, so the single-precision exchanges
+// move both components in ONE round through the same conflict-free layouts; its twiddles come
+// from a float2 copy of the tables (a double -> float conversion costs as much as four FMAs).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -32,34 +38,69 @@
 
 namespace psfr {
 
-PSFR_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-PSFR_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-PSFR_HD double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+template <class Z>
+struct ZTraits;
+template <>
+struct ZTraits<double2> {
+    using S = double;   // scalar
+    using W = double;   // shared-memory exchange word: one component per round
+    static constexpr int Rounds = 2;
+};
+template <>
+struct ZTraits<float2> {
+    using S = float;
+    using W = float2;   // both components in one 8-byte word, one round
+    static constexpr int Rounds = 1;
+};
+template <class Z>
+PSFR_HD Z mkz(typename ZTraits<Z>::S x, typename ZTraits<Z>::S y) {
+    Z r;
+    r.x = x;
+    r.y = y;
+    return r;
 }
+// twiddle table entry (double2, or float2 from the pre-rounded single-precision table) in the
+// transform's precision
+template <class Z, class TW>
+PSFR_HD Z ztw(const TW& w) {
+    using S = typename ZTraits<Z>::S;
+    return mkz<Z>((S)w.x, (S)w.y);
+}
+
+template <class Z>
+PSFR_HD Z cadd(Z a, Z b) { return mkz<Z>(a.x + b.x, a.y + b.y); }
+template <class Z>
+PSFR_HD Z csub(Z a, Z b) { return mkz<Z>(a.x - b.x, a.y - b.y); }
+template <class Z>
+PSFR_HD Z cmul(Z a, Z b) { return mkz<Z>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * i and a * (-i)
-PSFR_HD double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }
-PSFR_HD double2 cmulni(double2 a) { return make_double2(a.y, -a.x); }
+template <class Z>
+PSFR_HD Z cmuli(Z a) { return mkz<Z>(-a.y, a.x); }
+template <class Z>
+PSFR_HD Z cmulni(Z a) { return mkz<Z>(a.y, -a.x); }
 
 // ---- small DFTs, sign +i:  X[k] = sum_n x[n] exp(+2 pi i n k / R) -------------------
-PSFR_HD void dft4(double2& x0, double2& x1, double2& x2, double2& x3) {
-    double2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = cmuli(csub(x1, x3));
+template <class Z>
+PSFR_HD void dft4(Z& x0, Z& x1, Z& x2, Z& x3) {
+    Z a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = cmuli(csub(x1, x3));
     x0 = cadd(a, c);
     x2 = csub(a, c);
     x1 = cadd(b, d);
     x3 = csub(b, d);
 }
 
-PSFR_HD void dft8(double2* x) {
-    const double h = 0.70710678118654752440;
-    double2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
-    double2 o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+template <class Z>
+PSFR_HD void dft8(Z* x) {
+    using S = typename ZTraits<Z>::S;
+    const S h = (S)0.70710678118654752440;
+    Z e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
+    Z o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
     dft4(e0, e1, e2, e3);
     dft4(o0, o1, o2, o3);
     // o_k *= w8^k, w8 = exp(+i pi/4)
-    o1 = make_double2(h * (o1.x - o1.y), h * (o1.x + o1.y));
+    o1 = mkz<Z>(h * (o1.x - o1.y), h * (o1.x + o1.y));
     o2 = cmuli(o2);
-    o3 = make_double2(-h * (o3.x + o3.y), h * (o3.x - o3.y));
+    o3 = mkz<Z>(-h * (o3.x + o3.y), h * (o3.x - o3.y));
     x[0] = cadd(e0, o0);
     x[4] = csub(e0, o0);
     x[1] = cadd(e1, o1);
@@ -70,37 +111,38 @@ PSFR_HD void dft8(double2* x) {
     x[7] = csub(e3, o3);
 }
 
-PSFR_HD void dft5(double2& x0, double2& x1, double2& x2, double2& x3, double2& x4) {
-    const double c1 = 0.30901699437494742410;   // cos(2pi/5)
-    const double c2 = -0.80901699437494742410;  // cos(4pi/5)
-    const double s1 = 0.95105651629515357212;   // sin(2pi/5)
-    const double s2 = 0.58778525229247312917;   // sin(4pi/5)
-    double2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-    double2 a1 = make_double2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-    double2 a2 = make_double2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-    double2 b1 = make_double2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    double2 b2 = make_double2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-    x0 = make_double2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+template <class Z>
+PSFR_HD void dft5(Z& x0, Z& x1, Z& x2, Z& x3, Z& x4) {
+    using S = typename ZTraits<Z>::S;
+    const S c1 = (S)0.30901699437494742410;   // cos(2pi/5)
+    const S c2 = (S)-0.80901699437494742410;  // cos(4pi/5)
+    const S s1 = (S)0.95105651629515357212;   // sin(2pi/5)
+    const S s2 = (S)0.58778525229247312917;   // sin(4pi/5)
+    Z t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+    Z a1 = mkz<Z>(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+    Z a2 = mkz<Z>(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+    Z b1 = mkz<Z>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+    Z b2 = mkz<Z>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    x0 = mkz<Z>(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
     x1 = cadd(a1, cmuli(b1));
     x4 = csub(a1, cmuli(b1));
     x2 = cadd(a2, cmuli(b2));
     x3 = csub(a2, cmuli(b2));
 }
 
-template <int RA>
-PSFR_HD void dft_small(double2* x);
-template <>
-PSFR_HD void dft_small<1>(double2*) {}
-template <>
-PSFR_HD void dft_small<2>(double2* x) {
-    double2 a = x[0];
-    x[0] = cadd(a, x[1]);
-    x[1] = csub(a, x[1]);
+template <int RA, class Z>
+PSFR_HD void dft_small(Z* x) {
+    static_assert(RA == 1 || RA == 2 || RA == 4 || RA == 8, "unsupported small radix");
+    if constexpr (RA == 2) {
+        Z a = x[0];
+        x[0] = cadd(a, x[1]);
+        x[1] = csub(a, x[1]);
+    } else if constexpr (RA == 4) {
+        dft4(x[0], x[1], x[2], x[3]);
+    } else if constexpr (RA == 8) {
+        dft8(x);
+    }
 }
-template <>
-PSFR_HD void dft_small<4>(double2* x) { dft4(x[0], x[1], x[2], x[3]); }
-template <>
-PSFR_HD void dft_small<8>(double2* x) { dft8(x); }
 
 __host__ __device__ constexpr int modinv(int a, int m) {
     for (int i = 1; i < m; ++i)
@@ -110,15 +152,15 @@ __host__ __device__ constexpr int modinv(int a, int m) {
 
 // Prime-factor (Good-Thomas) DFT of length R3 = 5 * RA, RA in {1,2,4,8}; natural order in
 // and out.  n = (5 na + RA nb) mod R3,  k = (5 inv5 ka + RA invRA kb) mod R3.
-template <int R3>
-PSFR_HD void dft_r3(double2* x) {
+template <int R3, class Z>
+PSFR_HD void dft_r3(Z* x) {
     constexpr int RA = R3 / 5;
     constexpr int I5 = (RA == 1) ? 0 : modinv(5 % RA == 0 ? 1 : 5 % RA, RA);
     constexpr int IA = modinv(RA % 5, 5);
-    double2 y[R3];
+    Z y[R3];
 #pragma unroll
     for (int nb = 0; nb < 5; ++nb) {
-        double2 z[RA];
+        Z z[RA];
 #pragma unroll
         for (int na = 0; na < RA; ++na) z[na] = x[(5 * na + RA * nb) % R3];
         dft_small<RA>(z);
@@ -151,42 +193,49 @@ PSFR_HD double comp_get(const double2& a, int c) { return c ? a.y : a.x; }
 PSFR_HD void comp_set(double2& a, int c, double v) {
     if (c) a.y = v; else a.x = v;
 }
+// exchange word of round c: component c of a double2, the whole float2
+PSFR_HD double word_get(const double2& a, int c) { return c ? a.y : a.x; }
+PSFR_HD void word_set(double2& a, int c, double v) {
+    if (c) a.y = v; else a.x = v;
+}
+PSFR_HD float2 word_get(const float2& a, int) { return a; }
+PSFR_HD void word_set(float2& a, int, float2 v) { a = v; }
 
-template <int R3>
-PSFR_HD void fft_pass1(double2* v, const double2* tw1, int t) {
+template <int R3, class Z, class TW>
+PSFR_HD void fft_pass1(Z* v, const TW* tw1, int t) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         dft8(v + j * 8);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1)
-            v[j * 8 + k1] = cmul(v[j * 8 + k1], tw1[(j * 7 + (k1 - 1)) * G::TL + t]);
+            v[j * 8 + k1] = cmul(v[j * 8 + k1], ztw<Z>(tw1[(j * 7 + (k1 - 1)) * G::TL + t]));
     }
 }
 
-template <int R3>
-PSFR_HD void fft_x1_store(const double2* v, double* sm, int t, int c) {
+template <int R3, class Z>
+PSFR_HD void fft_x1_store(const Z* v, typename ZTraits<Z>::W* sm, int t, int c) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j)
 #pragma unroll
-        for (int k1 = 0; k1 < 8; ++k1) sm[k1 * G::S1 + t + G::TL * j] = comp_get(v[j * 8 + k1], c);
+        for (int k1 = 0; k1 < 8; ++k1) sm[k1 * G::S1 + t + G::TL * j] = word_get(v[j * 8 + k1], c);
 }
 
-template <int R3>
-PSFR_HD void fft_x1_load(double2* v, const double* sm, int t, int c) {
+template <int R3, class Z>
+PSFR_HD void fft_x1_load(Z* v, const typename ZTraits<Z>::W* sm, int t, int c) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int p = t + G::TL * j;
         const int base = (p % 8) * G::S1 + (p / 8);
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) comp_set(v[j * 8 + n2], c, sm[base + n2 * R3]);
+        for (int n2 = 0; n2 < 8; ++n2) word_set(v[j * 8 + n2], c, sm[base + n2 * R3]);
     }
 }
 
-template <int R3>
-PSFR_HD void fft_pass2(double2* v, const double2* tw2, int t) {
+template <int R3, class Z, class TW>
+PSFR_HD void fft_pass2(Z* v, const TW* tw2, int t) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -194,12 +243,12 @@ PSFR_HD void fft_pass2(double2* v, const double2* tw2, int t) {
         dft8(v + j * 8);
 #pragma unroll
         for (int k2 = 1; k2 < 8; ++k2)
-            v[j * 8 + k2] = cmul(v[j * 8 + k2], tw2[(k2 - 1) * R3 + n3]);
+            v[j * 8 + k2] = cmul(v[j * 8 + k2], ztw<Z>(tw2[(k2 - 1) * R3 + n3]));
     }
 }
 
-template <int R3>
-PSFR_HD void fft_x2_store(const double2* v, double* sm, int t, int c) {
+template <int R3, class Z>
+PSFR_HD void fft_x2_store(const Z* v, typename ZTraits<Z>::W* sm, int t, int c) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -207,22 +256,22 @@ PSFR_HD void fft_x2_store(const double2* v, double* sm, int t, int c) {
         const int n3 = p / 8;
         const int base = 64 * n3 + ((p % 8) ^ (8 * (n3 & 1)));
 #pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) sm[base ^ (8 * k2)] = comp_get(v[j * 8 + k2], c);   // q = k1 + 8 k2
+        for (int k2 = 0; k2 < 8; ++k2) sm[base ^ (8 * k2)] = word_get(v[j * 8 + k2], c);   // q = k1 + 8 k2
     }
 }
 
-template <int R3>
-PSFR_HD void fft_x2_load(double2* v, const double* sm, int t, int c) {
+template <int R3, class Z>
+PSFR_HD void fft_x2_load(Z* v, const typename ZTraits<Z>::W* sm, int t, int c) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int u = 0; u < G::NQ; ++u)
 #pragma unroll
         for (int n3 = 0; n3 < R3; ++n3)
-            comp_set(v[u * R3 + n3], c, sm[64 * n3 + ((t + G::TL * u) ^ (8 * (n3 & 1)))]);
+            word_set(v[u * R3 + n3], c, sm[64 * n3 + ((t + G::TL * u) ^ (8 * (n3 & 1)))]);
 }
 
-template <int R3>
-PSFR_HD void fft_pass3(double2* v) {
+template <int R3, class Z>
+PSFR_HD void fft_pass3(Z* v) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int u = 0; u < G::NQ; ++u) dft_r3<R3>(v + u * R3);
@@ -231,15 +280,15 @@ PSFR_HD void fft_pass3(double2* v) {
 // skewed natural-order address of output k (conflict-free dump and strided gathers)
 PSFR_HD int nat_addr(int k) { return k + (k >> 4); }
 
-template <int R3>
-PSFR_HD void fft_dump(const double2* v, double* sm, int t, int c) {
+template <int R3, class Z>
+PSFR_HD void fft_dump(const Z* v, typename ZTraits<Z>::W* sm, int t, int c) {
     using G = FftGeom<R3>;
 #pragma unroll
     for (int u = 0; u < G::NQ; ++u)
 #pragma unroll
         for (int k3 = 0; k3 < R3; ++k3)
             // nat_addr(t + c) = nat_addr(t) + c + c/16 for c a multiple of 16: constant offsets
-            sm[nat_addr(t) + (G::TL * u + 64 * k3) + ((G::TL * u + 64 * k3) >> 4)] = comp_get(v[u * R3 + k3], c);
+            sm[nat_addr(t) + (G::TL * u + 64 * k3) + ((G::TL * u + 64 * k3) >> 4)] = word_get(v[u * R3 + k3], c);
 }
 
 // Twiddle tables (host fills them in double precision; see psfr_api.cu / host_check.cu)
@@ -248,12 +297,13 @@ PSFR_HD void fft_dump(const double2* v, double* sm, int t, int c) {
 #ifdef __CUDACC__
 // The whole transform for one warp (device).  v: 40 points in the "load" layout on entry,
 // in the "result" layout on exit.  sm: warp-private buffer of FftGeom<R3>::XBUF doubles.
-template <int R3>
-__device__ __forceinline__ void warp_fft(double2* v, double* sm, const double2* tw1,
-                                         const double2* tw2, int t) {
+template <int R3, class Z, class TW>
+__device__ __forceinline__ void warp_fft(Z* v, double* sm_raw, const TW* tw1, const TW* tw2, int t) {
+    using W = typename ZTraits<Z>::W;
+    W* sm = reinterpret_cast<W*>(sm_raw);
     fft_pass1<R3>(v, tw1, t);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < ZTraits<Z>::Rounds; ++c) {
         fft_x1_store<R3>(v, sm, t, c);
         __syncwarp();
         fft_x1_load<R3>(v, sm, t, c);
@@ -261,7 +311,7 @@ __device__ __forceinline__ void warp_fft(double2* v, double* sm, const double2* 
     }
     fft_pass2<R3>(v, tw2, t);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < ZTraits<Z>::Rounds; ++c) {
         fft_x2_store<R3>(v, sm, t, c);
         __syncwarp();
         fft_x2_load<R3>(v, sm, t, c);

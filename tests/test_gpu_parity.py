@@ -256,6 +256,35 @@ def test_underflow_cut_is_invisible(psfrec):
         assert_image_close(full[k], ref[k])
 
 
+@pytest.mark.parametrize('seeing,L0,GL', [(1.68, 19.9, 0.36), (1.57, 28.0, 0.88), (0.91, 16.9, 0.71)])
+def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
+    """Row pairs whose every OTF entry is below e^-30 of the peak are evaluated and transformed
+    in single precision, blocks below e^-25 use the single-precision exp (psfr.h,
+    PSFR_OPT_F32_ROWS / PSFR_OPT_EXP_GRADE).  The result must equal the all-FP64 evaluation
+    to FP64 rounding of the peak and the oracle to the PSF tolerance."""
+    from muse_psfr_b200 import _lib
+    psd = orc.simul_psd_wfm([GL, 1 - GL], (100, 10000), seeing, L0)
+    lam = np.array([490., 640., 780., 930.])
+    ref = orc.psf_muse(psd, lam)
+    ctx = psfrec.get_context()
+    try:
+        ctx.set_option(_lib.OPT_EXP_GRADE, 1e30)
+        ctx.set_option(_lib.OPT_F32_ROWS, 1e30)
+        full = psfrec.psf_muse(psd, lam)
+    finally:
+        ctx.set_option(_lib.OPT_EXP_GRADE, 25.0)
+        ctx.set_option(_lib.OPT_F32_ROWS, 30.0)
+    graded = psfrec.psf_muse(psd, lam)
+    # the graded paths really ran: some row has all its entries between e^-64 and e^-30 at 490 nm
+    d = ctx.get_structure_function(0)
+    x = 0.5 * (2 * np.pi / 490.) ** 2 * d[:641].min(axis=1)
+    assert ((x >= 30) & (x < 64)).any()
+    assert rel_to_peak(graded, full) < 1e-13
+    for k in range(lam.size):
+        assert_image_close(graded[k], ref[k])
+        assert_image_close(full[k], ref[k])
+
+
 def test_wavelength_below_grid_limit(psfrec, psd1):
     with pytest.raises(ValueError):
         psfrec.psf_muse(psd1[0], np.array([400.]))      # needs a 1552-pixel crop: reference fails too
@@ -441,6 +470,8 @@ def test_c_abi_argument_errors(psfrec):
                                   _lib.ptr(out), None, None) == _lib.E_ARG
     assert lib.psfr_set_option(ctx._h, 99, 1.0) == _lib.E_ARG
     assert lib.psfr_set_option(ctx._h, _lib.OPT_EXP_CUT, -1.0) == _lib.E_ARG
+    assert lib.psfr_set_option(ctx._h, _lib.OPT_EXP_GRADE, 0.0) == _lib.E_ARG
+    assert lib.psfr_set_option(ctx._h, _lib.OPT_F32_ROWS, -3.0) == _lib.E_ARG
     assert lib.psfr_psf_cube(ctx._h, 1, 1, ctx.max_lambda + 1, _lib.ptr(np.full(ctx.max_lambda + 1, 600.)),
                              _lib.ptr(out), None) < 0
     with pytest.raises(_lib.PsfrError):
