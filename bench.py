@@ -261,8 +261,8 @@ def run_gpu(args):
                    'graded_precision': 'row pairs entirely below exp(-%g) of the OTF peak are evaluated and transformed '
                                        'in FP32, blocks entirely below exp(-%g) use the FP32 exp; everything else '
                                        'FP64 (psfr.h PSFR_OPT_F32_ROWS / PSFR_OPT_EXP_GRADE; parity tests hold the '
-                                       '1e-9 PSF bar)' % (30.0 if args.f32_rows is None else args.f32_rows,
-                                                          25.0 if args.grade is None else args.grade),
+                                       '1e-9 PSF bar)' % (25.0 if args.f32_rows is None else args.f32_rows,
+                                                          20.0 if args.grade is None else args.grade),
                    'results_finite': finite},
         'e2e': {'value': e2e, 'unit': 'PSF/s',
                 'h2d_bytes_per_step': int(recs.nbytes + dirs.nbytes + pos.nbytes + LBDA.nbytes),

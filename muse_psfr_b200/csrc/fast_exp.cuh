@@ -40,7 +40,7 @@ __device__ __forceinline__ double fast_exp(double x) {
 }
 
 // 2^x on the special-function unit (MUFU.EX2), relative error 2^-22; flushes to zero below 2^-126.
-// Used only where the result is below exp(-25) of the OTF peak (psfr_hot.cu).
+// Used only where the result is below exp(-20) of the OTF peak (psfr_hot.cu).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -85,11 +85,18 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     }
     if (c->NF == 2)
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_wsamp, ws.data(), ws.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
+    // the row kernel classifies the units of a row pair by c_lambda * min(D): sorted copy + permutation
+    std::vector<int> order(nlam);
+    for (int l = 0; l < nlam; ++l) order[l] = l;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cl[a] > cl[b]; });
+    std::vector<double> csort(nlam);
+    for (int l = 0; l < nlam; ++l) csort[l] = cl[order[l]];
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_csort, csort.data(), nlam * sizeof(double), cudaMemcpyHostToDevice, s));
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_lorder, order.data(), nlam * sizeof(int), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_lam, cl.data(), nlam * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_frac, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kidx, kx.data(), kx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));   // the host vectors go out of scope
-    c->clam_min = *std::min_element(cl.begin(), cl.end());
     return PSFR_OK;
 }
 
@@ -169,7 +176,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
-    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32);
+    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_csort); cudaFree(c->d_lorder);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -257,6 +264,8 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_draws, P * PSFR_DRAW_NPAR));
     CK(dev_alloc(c, &c->d_misc, (size_t)misc_size(max_planes)));
     CK(dev_alloc(c, &c->d_lam, LM));
+    CK(dev_alloc(c, &c->d_csort, LM));
+    CK(dev_alloc(c, &c->d_lorder, LM));
     CK(dev_alloc(c, &c->d_kidx, LM * kNS));
     CK(dev_alloc(c, &c->d_frac, LM * kPSF));
     CK(dev_alloc(c, &c->d_kern_tt, P * kKW * kKW));

@@ -19,8 +19,9 @@
 #include "fast_exp.cuh"
 #include "tma.cuh"
 
-#ifndef PSFR_HOT_BLK
-#define PSFR_HOT_BLK 4
+// warps per lockstep group of the row kernel (see hot_rows_kernel)
+#ifndef PSFR_HOT_GROUP
+#define PSFR_HOT_GROUP 8
 #endif
 
 namespace psfr {
@@ -57,7 +58,8 @@ struct HotParams {
     const float* D32;      // single-precision copies of D and T (dim 1280)
     const float* T32;
     const float2* tw32;    // single-precision twiddles (global memory, L1-resident)
-    double cmin;           // smallest c_lambda: a row pair with cmin * min(D) > cut is dead at every wavelength
+    const double* csort;   // [nlam] c_lambda in descending order
+    const int* lorder;     // [nlam] wavelength index of sorted position i
     int* next_item;        // work counter, zeroed before the launch
     double cut;            // OTF entries with c*D > cut (exp < e^-cut) are flushed to zero
     double grade;          // blocks whose live entries all have c*D >= grade take the single-precision exp
@@ -78,8 +80,10 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);   // per-stage count of warps done with it
     volatile int* item_of = released + kStages;               // per-stage work item (-1: no more work)
+    volatile int* la_of = item_of + kStages;                  // per-stage: sorted positions [0, la) are dead,
+    volatile int* lb_of = la_of + kStages;                    //   [la, lb) single precision, [lb, nlam) FP64
     volatile double* dmin_of = reinterpret_cast<volatile double*>(smem_raw + 64);   // per-stage min(D) of the row pair
-    static_assert(kStages <= 4, "the 128-byte header holds four stages");
+    static_assert(kStages == 2, "the 128-byte header is laid out for two stages");
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
     double* ring = reinterpret_cast<double*>(tw2 + G::TW2);   // [stage][D | T | D32 | T32]
@@ -98,12 +102,27 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             const int plane = item / kPairs, rp = item % kPairs;
             double* dst = ring + (size_t)s * kStageDoubles;
             item_of[s] = item;
-            // a row pair that is below the cut at the longest wavelength is below it at all of
-            // them: the consumers only write zeros and never look at the stage
             const double dm = fmin(__ldg(p.dmin + (size_t)plane * kRows + 2 * rp),
                                    __ldg(p.dmin + (size_t)plane * kRows + 2 * rp + 1));
-            dmin_of[s] = dm;   // travels with the item id: the consumers need it before anything else
-            if (p.cmin * dm > p.cut) {
+            dmin_of[s] = dm;   // travels with the item id
+            // Classes of the item's nlam units, by binary search on the descending c_lambda:
+            // c * min(D) > cut -> dead (the transform of both rows is zero), >= f32_min ->
+            // single precision, else FP64.  Both predicates are monotone along the sorted order.
+            int lo = 0, hi = p.nlam;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(p.csort + mid) * dm > p.cut) lo = mid + 1; else hi = mid;
+            }
+            const int la = lo;
+            hi = p.nlam;
+            while (C::F32 && lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(p.csort + mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
+            }
+            la_of[s] = la;
+            lb_of[s] = lo;
+            // dead at every wavelength: the consumers only write zeros and never look at the stage
+            if (la == p.nlam) {
                 mbar_arrive(full + s);
                 return;
             }
@@ -135,13 +154,16 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     __syncthreads();
 
     double* xb = xall + (size_t)warp * G::XBUF;
-    // Units (item, wavelength) are numbered g = seq * nlam + lam in the order in which this CTA
-    // receives its items (seq = 0, 1, ...) and dealt to the warps in ROUNDS of eight: warp w
-    // takes unit 8 R + w of round R, and all warps enter a round together (one CTA barrier).
-    // The unit body is ~70 KB of straight-line code, far more than the instruction caches
-    // hold; warps that run it side by side share every fetched line, warps that drift apart
-    // each stream it from L2 on their own (ncu: `no_instruction` was the top stall and FP32
-    // units, whose code adds 40 KB, made the kernel slower until the rounds were aligned).
+    // The LIVE units of this CTA form a stream: item after item in the order in which the CTA
+    // receives them (seq = 0, 1, ...), within an item the sorted positions la .. nlam-1
+    // (reversed for odd seq, so that the class changes only once per item along the stream).
+    // The stream is dealt to the warps in ROUNDS of eight consecutive units and all warps
+    // enter a round together (one CTA barrier): the unit body is ~70 KB of straight-line code
+    // (+ 40 KB for the single-precision class), far more than the instruction caches hold;
+    // warps that run it side by side share every fetched line, warps that drift apart each
+    // stream it from L2 on their own (ncu: `no_instruction` was the top stall of the
+    // free-running version).  Dead units are not part of the stream: whoever passes an item
+    // zeroes its share of them.
     //
     // A warp passes through EVERY item in order - wait for its fill, release it when its next
     // unit lies in a later item - also when it has no unit in it: that keeps all warps within
@@ -149,18 +171,40 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     // rely on.  Fills are issued in order, so the first -1 is followed by -1 only and no TMA
     // is in flight when the CTA retires.
     int cur = 0;            // sequence number of the item this warp is in
-    bool seen = false;      // its fill has been observed
-    auto enter = [&](int seq) {
+    bool seen = false;      // its fill has been observed (and this warp's dead units zeroed)
+    int base = 0;           // stream offset of the round's first unit, relative to item cur's first live unit
+    // move to the item that holds stream offset `rel` (relative to item cur); false: the stream ended
+    auto seek = [&](int& rel) -> bool {
         while (true) {
+            const int s = cur % kStages;
             if (!seen) {
-                mbar_wait(full + cur % kStages, (cur / kStages) & 1);
+                mbar_wait(full + s, (cur / kStages) & 1);
                 seen = true;
+                const int item = item_of[s];
+                if (item >= 0) {
+                    const int plane = item / kPairs, rp = item % kPairs, la = la_of[s];
+                    for (int i = warp; i < la; i += kHotWarps) {
+                        double2* out = p.Y + ((size_t)plane * p.nlam + __ldg(p.lorder + i)) * kNS * kRows + 2 * rp;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int y = lane + 32 * k;
+                            if (y < kNS) {
+                                double2* o = out + (size_t)y * kRows;
+                                o[0] = make_double2(0.0, 0.0);
+                                o[1] = make_double2(0.0, 0.0);
+                            }
+                        }
+                    }
+                }
             }
-            if (cur == seq) break;
+            if (item_of[s] < 0) return false;
+            const int n = p.nlam - la_of[s];
+            if (rel < n) return true;
+            rel -= n;
+            base -= n;
             // release the stage; the last warp to do so refills it with the next work item
             __syncwarp();
             if (lane == 0) {
-                const int s = cur % kStages;
                 __threadfence_block();
                 const int old = atomicAdd(released + s, 1);
                 if (old == kHotWarps - 1) {
@@ -174,53 +218,31 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             ++cur;
             seen = false;
         }
-        return item_of[cur % kStages];
     };
-    // A round must not span more items than the ring has stages (its later units would wait for
-    // a fill that needs the release of its earlier ones): with rs <= nlam units per round it
-    // spans at most two.  Warps beyond rs (only when nlam < 8) idle through the rounds.
-    const int rs = p.nlam < kHotWarps ? p.nlam : kHotWarps;
-    int seq0 = 0, lam0 = 0;   // (item, wavelength) of the round's first unit, advanced without divisions
+    constexpr int kGroup = PSFR_HOT_GROUP < kHotWarps ? PSFR_HOT_GROUP : kHotWarps;
+    base = (warp / kGroup) * kGroup;   // stream offset of the group's first unit of the round
+    int rel0 = base;
+    bool more = seek(rel0);
 #pragma unroll 1
     for (;;) {
-        __syncthreads();
-        // the round's first unit decides for everybody: items only get later within a round
-        if (enter(seq0) < 0) break;
-        int seq = seq0, lam = lam0 + warp;
-        if (lam >= p.nlam) {
-            lam -= p.nlam;
-            ++seq;
-        }
-        const int item = warp < rs ? enter(seq) : -1;
-        lam0 += rs;
-        if (lam0 >= p.nlam) {
-            lam0 -= p.nlam;
-            ++seq0;
-        }
-        if (item >= 0) {
-            const int s = seq % kStages;
+        // one barrier per lockstep group (kGroup consecutive warps = one warp per scheduler)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / kGroup), "n"(kGroup * 32) : "memory");
+        if (!more) break;   // the group's first unit decides for the group: the stream only gets later
+        int rel = base + warp % kGroup;
+        if (seek(rel)) {
+            const int s = cur % kStages;
+            const int item = item_of[s];
+            const int pos = (cur & 1) ? p.nlam - 1 - rel : la_of[s] + rel;   // sorted position of the unit
+            const bool f32_unit = C::F32 && pos < lb_of[s];
+            const int lam = __ldg(p.lorder + pos);
             const double* sD = ring + (size_t)s * kStageDoubles;
             const double* sT = sD + kTile;
             const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);   // dim 1280 only
             const float* sT32 = sD32 + kTile;
             const int plane = item / kPairs, rp = item % kPairs;
-            const double dm = dmin_of[s];
-            do {   // one unit; `continue` leaves it
+            {
                 const double cl = __ldg(p.clam + lam);
                 double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
-                if (cl * dm > p.cut) {
-                    // both rows are below the cut everywhere: their transform is zero
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int y = lane + 32 * i;
-                        if (y < kNS) {
-                            double2* o = out + (size_t)y * kRows;
-                            o[0] = make_double2(0.0, 0.0);
-                            o[1] = make_double2(0.0, 0.0);
-                        }
-                    }
-                    continue;
-                }
                 const double negc = -cl;
                 // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
                 const uint16_t* kx = p.kidx + (size_t)lam * kNS;
@@ -234,10 +256,10 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 const float negc2f = (float)(negc * 1.44269504088896338700);   // exp(-c D) = 2^(negc2f D)
                 const int cut32 = __float_as_int((float)(p.cut / cl));
                 const int grade32 = __float_as_int((float)(p.grade / cl));
-                if (C::F32 && cl * dm >= p.f32_min) {
+                if (f32_unit) {
                     // ---- single-precision unit: every entry of both rows is below exp(-f32_min)
-                    // (default e^-30 = 9.4e-14) of the OTF peak, so a relative error of 1e-6 in this
-                    // unit's contribution is < 1e-19 of the peak: exp (MUFU ex2), the products and
+                    // (default e^-25 = 1.4e-11) of the OTF peak, so a relative error of 1e-6 in this
+                    // unit's contribution is < 1e-17 of the peak: exp (MUFU ex2), the products and
                     // the transform run in FP32, off the FP64 pipe, from the FP32 copies of D and T.
                     float2 vf[40];
 #pragma unroll
@@ -284,9 +306,9 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     // j*8 + n1, j = 0..4): ten independent exp chains per lane.  Three grades,
                     // chosen per block by a warp vote on the FP32 copies: dead (outside the pupil-
                     // autocorrelation support, where the OTF is exactly zero, or below the underflow
-                    // cut) -> zeros; every live entry below exp(-grade) (default e^-25 = 1.4e-11 of
+                    // cut) -> zeros; every live entry below exp(-grade) (default e^-20 = 2.1e-9 of
                     // the peak) -> MUFU ex2 and the product in single precision, absolute error
-                    // < 1e-16 of the peak; else FP64 values from the ring and the full FP64 exp.
+                    // < 1e-14 of the peak; else FP64 values from the ring and the full FP64 exp.
 #pragma unroll
                     for (int n1 = 0; n1 < 8; ++n1) {
                         bool dead = true, cheap = true;
@@ -403,11 +425,13 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         o[1] = make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x));
                     }
                 }
-            } while (false);
+            }
         }
-        // leave the items that lie wholly before the next round BEFORE its barrier, so that
-        // their stages can be refilled while the slower warps finish this round
-        enter(seq0);
+        // move on to the next round's first unit BEFORE its barrier: the items that lie wholly
+        // before it are released and can be refilled while the slower warps finish this round
+        base += kHotWarps;
+        rel0 = base;
+        more = seek(rel0);
     }
 }
 
@@ -554,7 +578,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
     HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_dphi32,
-                c->d_otf32, c->d_tw32, c->clam_min, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
+                c->d_otf32, c->d_tw32, c->d_csort, c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));

@@ -66,11 +66,12 @@ struct Ctx {
     float* d_dphi32 = nullptr;   // [max_planes][rows][N] single-precision copy of d_dphi (dim 1280: block grading + FP32 row pairs)
     float* d_otf32 = nullptr;    // [rows][N] single-precision copy of d_otf
     float2* d_tw32 = nullptr;    // twiddles of d_tw rounded to single precision
-    double clam_min = 0.0;       // smallest c_lambda of the current wavelength table
+    double* d_csort = nullptr;   // [max_lambda] c_lambda in descending order (unit classes of the row kernel)
+    int* d_lorder = nullptr;     // [max_lambda] wavelength index of sorted position i
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
-    double exp_grade = 25.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
-    double f32_rows = 30.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
+    double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
+    double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples

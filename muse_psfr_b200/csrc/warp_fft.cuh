@@ -27,7 +27,7 @@
 // same code lane by lane on the CPU.
 //
 // The transform is templated on the complex type Z: double2 (the product path) or float2, which
-// the stage-B row kernel uses for row pairs whose every entry is below exp(-30) of the OTF peak
+// the stage-B row kernel uses for row pairs whose every entry is below exp(-25) of the OTF peak
 // (psfr_hot.cu).  A float2 is one 8-byte shared-memory word, so the single-precision exchanges
 // move both components in ONE round through the same conflict-free layouts; its twiddles come
 // from a float2 copy of the tables (a double -> float conversion costs as much as four FMAs).

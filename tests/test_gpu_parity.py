@@ -258,8 +258,8 @@ def test_underflow_cut_is_invisible(psfrec):
 
 @pytest.mark.parametrize('seeing,L0,GL', [(1.68, 19.9, 0.36), (1.57, 28.0, 0.88), (0.91, 16.9, 0.71)])
 def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
-    """Row pairs whose every OTF entry is below e^-30 of the peak are evaluated and transformed
-    in single precision, blocks below e^-25 use the single-precision exp (psfr.h,
+    """Row pairs whose every OTF entry is below e^-25 of the peak are evaluated and transformed
+    in single precision, blocks below e^-20 use the single-precision exp (psfr.h,
     PSFR_OPT_F32_ROWS / PSFR_OPT_EXP_GRADE).  The result must equal the all-FP64 evaluation
     to FP64 rounding of the peak and the oracle to the PSF tolerance."""
     from muse_psfr_b200 import _lib
@@ -272,13 +272,13 @@ def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
         ctx.set_option(_lib.OPT_F32_ROWS, 1e30)
         full = psfrec.psf_muse(psd, lam)
     finally:
-        ctx.set_option(_lib.OPT_EXP_GRADE, 25.0)
-        ctx.set_option(_lib.OPT_F32_ROWS, 30.0)
+        ctx.set_option(_lib.OPT_EXP_GRADE, 20.0)
+        ctx.set_option(_lib.OPT_F32_ROWS, 25.0)
     graded = psfrec.psf_muse(psd, lam)
-    # the graded paths really ran: some row has all its entries between e^-64 and e^-30 at 490 nm
+    # the graded paths really ran: some row has all its entries between e^-64 and e^-25 at 490 nm
     d = ctx.get_structure_function(0)
     x = 0.5 * (2 * np.pi / 490.) ** 2 * d[:641].min(axis=1)
-    assert ((x >= 30) & (x < 64)).any()
+    assert ((x >= 25) & (x < 64)).any()
     assert rel_to_peak(graded, full) < 1e-13
     for k in range(lam.size):
         assert_image_close(graded[k], ref[k])
