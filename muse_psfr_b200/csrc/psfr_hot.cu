@@ -40,8 +40,10 @@ struct HotCfg {
     static constexpr uint32_t TileBytes = Tile * sizeof(double);
     static constexpr uint32_t TileBytes32 = Tile * sizeof(float);
     static constexpr uint32_t StageBytes = 2 * TileBytes + (F32 ? 2 * TileBytes32 : 0);
+    static constexpr int TabMax = 64;                // wavelength tables up to this size are staged in shared memory
+    static constexpr size_t TabBytes = TabMax * (2 * sizeof(double) + sizeof(int));
     static constexpr size_t Smem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
-                                   (size_t)Stages * StageBytes + (size_t)Warps * G::XBUF * sizeof(double);
+                                   (size_t)Stages * StageBytes + (size_t)Warps * G::XBUF * sizeof(double) + TabBytes;
     static_assert(Smem <= 232448, "hot kernel shared memory exceeds the 227 KB per-CTA limit");
 };
 
@@ -90,6 +92,13 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     double* xall = ring + (size_t)kStages * kStageDoubles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.nplanes * kPairs;
+    // per-wavelength scalars in sorted order (c, 1/c, wavelength index): every unit starts with
+    // them, and in lockstep nobody hides a trip to L2 - staged here when they fit
+    double* tab_c = xall + (size_t)kHotWarps * G::XBUF;
+    double* tab_rc = tab_c + C::TabMax;
+    int* tab_lo = reinterpret_cast<int*>(tab_rc + C::TabMax);
+    const bool tabbed = p.nlam <= C::TabMax;
+    auto c_of = [&](int pos) { return tabbed ? tab_c[pos] : __ldg(p.csort + pos); };
 
     // Work items (plane, row pair) are handed out by a global counter: with the underflow cut
     // the cost of an item ranges from "write zeros" to nlam full transforms, so a static
@@ -111,13 +120,13 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             int lo = 0, hi = p.nlam;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (__ldg(p.csort + mid) * dm > p.cut) lo = mid + 1; else hi = mid;
+                if (c_of(mid) * dm > p.cut) lo = mid + 1; else hi = mid;
             }
             const int la = lo;
             hi = p.nlam;
             while (C::F32 && lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (__ldg(p.csort + mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
+                if (c_of(mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
             }
             la_of[s] = la;
             lb_of[s] = lo;
@@ -142,6 +151,14 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     };
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
+    if (tabbed)
+        for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
+            const double cv = __ldg(p.csort + i);
+            tab_c[i] = cv;
+            tab_rc[i] = 1.0 / cv;
+            tab_lo[i] = __ldg(p.lorder + i);
+        }
+    __syncthreads();   // the first issue() below reads the table
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full + s, 1);
@@ -184,14 +201,12 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 if (item >= 0) {
                     const int plane = item / kPairs, rp = item % kPairs, la = la_of[s];
                     for (int i = warp; i < la; i += kHotWarps) {
-                        double2* out = p.Y + ((size_t)plane * p.nlam + __ldg(p.lorder + i)) * kNS * kRows + 2 * rp;
+                        double2* out = p.Y + ((size_t)plane * p.nlam + (tabbed ? tab_lo[i] : __ldg(p.lorder + i))) * kNS * kRows + 2 * rp;
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
                             const int y = lane + 32 * k;
                             if (y < kNS) {
-                                double2* o = out + (size_t)y * kRows;
-                                o[0] = make_double2(0.0, 0.0);
-                                o[1] = make_double2(0.0, 0.0);
+                                st_global_256(out + (size_t)y * kRows, make_double2(0.0, 0.0), make_double2(0.0, 0.0));
                             }
                         }
                     }
@@ -234,14 +249,14 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             const int item = item_of[s];
             const int pos = (cur & 1) ? p.nlam - 1 - rel : la_of[s] + rel;   // sorted position of the unit
             const bool f32_unit = C::F32 && pos < lb_of[s];
-            const int lam = __ldg(p.lorder + pos);
+            const int lam = tabbed ? tab_lo[pos] : __ldg(p.lorder + pos);
+            const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
             const double* sD = ring + (size_t)s * kStageDoubles;
             const double* sT = sD + kTile;
             const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);   // dim 1280 only
             const float* sT32 = sD32 + kTile;
             const int plane = item / kPairs, rp = item % kPairs;
             {
-                const double cl = __ldg(p.clam + lam);
                 double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
                 const double negc = -cl;
                 // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
@@ -254,8 +269,8 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 // float (double) orders like its bit pattern (high word); the SIGNED compare keeps a
                 // D rounded slightly below zero alive.
                 const float negc2f = (float)(negc * 1.44269504088896338700);   // exp(-c D) = 2^(negc2f D)
-                const int cut32 = __float_as_int((float)(p.cut / cl));
-                const int grade32 = __float_as_int((float)(p.grade / cl));
+                const int cut32 = __float_as_int((float)(p.cut * rcl));
+                const int grade32 = __float_as_int((float)(p.grade * rcl));
                 if (f32_unit) {
                     // ---- single-precision unit: every entry of both rows is below exp(-f32_min)
                     // (default e^-25 = 1.4e-11) of the OTF peak, so a relative error of 1e-6 in this
@@ -331,7 +346,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                                 }
                             }
                         } else {
-                            const int cut_hi = __double2hiint(p.cut / cl);
+                            const int cut_hi = __double2hiint(p.cut * rcl);
                             cheap = false;
 #pragma unroll
                             for (int j = 0; j < 5; ++j) {
@@ -420,9 +435,9 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 for (int i = 0; i < 3; ++i) {
                     const int y = lane + 32 * i;
                     if (y < kNS) {
-                        double2* o = out + (size_t)y * kRows;
-                        o[0] = make_double2(0.5 * (za[i].x + zb[i].x), 0.5 * (za[i].y - zb[i].y));
-                        o[1] = make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x));
+                        st_global_256(out + (size_t)y * kRows,
+                                      make_double2(0.5 * (za[i].x + zb[i].x), 0.5 * (za[i].y - zb[i].y)),
+                                      make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x)));
                     }
                 }
             }

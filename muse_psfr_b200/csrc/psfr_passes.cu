@@ -243,8 +243,8 @@ struct StoreTransposedPair {
             const int y = lane + 32 * i;
             const double2 za = nat_get<NF>(xb, y), zb = nat_get<NF>(xb, (D::N - y) % D::N);
             double2* o = out + (size_t)y * D::Rows;
-            o[0] = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
-            o[1] = make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x));
+            st_global_256(o, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                          make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
         }
     }
 };

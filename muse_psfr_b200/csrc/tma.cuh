@@ -1,4 +1,5 @@
-// mbarrier + TMA bulk-copy helpers (cp.async.bulk global -> shared with complete_tx; SASS UBLKCP).
+// mbarrier + TMA bulk-copy helpers (cp.async.bulk global -> shared with complete_tx; SASS UBLKCP)
+// and the 256-bit global store.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -37,6 +38,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// One 32-byte global store (sm_100: STG.E.ENL2.256): two adjacent double2, 32-byte aligned.  The
+// pass kernels write their transposed output as one full 32-byte sector per frequency.
+__device__ __forceinline__ void st_global_256(double2* p, double2 a, double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y)
+                 : "memory");
 }
 
 }  // namespace psfr
