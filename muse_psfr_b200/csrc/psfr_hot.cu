@@ -84,6 +84,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     volatile int* item_of = released + kStages;               // per-stage work item (-1: no more work)
     volatile int* la_of = item_of + kStages;                  // per-stage: sorted positions [0, la) are dead,
     volatile int* lb_of = la_of + kStages;                    //   [la, lb) single precision, [lb, nlam) FP64
+    volatile int* ns_of = lb_of + kStages;                    // per-stage number of stream slots of the item
     volatile double* dmin_of = reinterpret_cast<volatile double*>(smem_raw + 64);   // per-stage min(D) of the row pair
     static_assert(kStages == 2, "the 128-byte header is laid out for two stages");
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
@@ -130,6 +131,9 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             }
             la_of[s] = la;
             lb_of[s] = lo;
+            // stream slots: one FP64 unit, or TWO single-precision units that run as the two
+            // halves of one packed transform
+            ns_of[s] = (lo - la + 1) / 2 + (p.nlam - lo);
             // dead at every wavelength: the consumers only write zeros and never look at the stage
             if (la == p.nlam) {
                 mbar_arrive(full + s);
@@ -213,7 +217,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 }
             }
             if (item_of[s] < 0) return false;
-            const int n = p.nlam - la_of[s];
+            const int n = ns_of[s];
             if (rel < n) return true;
             rel -= n;
             base -= n;
@@ -247,17 +251,113 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
         if (seek(rel)) {
             const int s = cur % kStages;
             const int item = item_of[s];
-            const int pos = (cur & 1) ? p.nlam - 1 - rel : la_of[s] + rel;   // sorted position of the unit
-            const bool f32_unit = C::F32 && pos < lb_of[s];
-            const int lam = tabbed ? tab_lo[pos] : __ldg(p.lorder + pos);
-            const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
+            // slot -> units (sorted positions): the first npair slots of an item hold two
+            // single-precision units each (the last one may hold one), the others one FP64 unit;
+            // odd items run their slots backwards
+            const int la = la_of[s], lb = lb_of[s], npair = (lb - la + 1) / 2;
+            const int slot = (cur & 1) ? ns_of[s] - 1 - rel : rel;
             const double* sD = ring + (size_t)s * kStageDoubles;
             const double* sT = sD + kTile;
             const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);   // dim 1280 only
             const float* sT32 = sD32 + kTile;
             const int plane = item / kPairs, rp = item % kPairs;
-            {
-                double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
+            auto lam_of = [&](int pos) { return tabbed ? tab_lo[pos] : __ldg(p.lorder + pos); };
+            auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp; };
+            // untangle the two packed real rows: row 2rp from the even, row 2rp+1 from the odd part
+            auto store_rows = [&](double2* out, int i, double2 za, double2 zb) {
+                if (lane + 32 * i < kNS)
+                    st_global_256(out + (size_t)(lane + 32 * i) * kRows,
+                                  make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                                  make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+            };
+            if (C::F32 && slot < npair) {
+                // ---- single-precision pair: every entry of both rows is below exp(-f32_min) (default
+                // e^-25 = 1.4e-11) of the OTF peak at BOTH wavelengths, so a relative error of 1e-6 in
+                // their contribution is < 1e-17 of the peak.  exp (MUFU ex2), the products and the
+                // transform run in FP32 from the FP32 copies of D and T, and the two wavelengths are
+                // the two halves of ONE packed transform (Z2: FADD2 / FMUL2 / FFMA2).
+                const int posA = la + 2 * slot;
+                const bool two = posA + 1 < lb;
+                const int posB = two ? posA + 1 : posA;
+                const int lamA = lam_of(posA), lamB = lam_of(posB);
+                const double cB = c_of(posB);
+                const float nA = (float)(-c_of(posA) * 1.44269504088896338700);   // exp(-c D) = 2^(n D)
+                const float nB = (float)(-cB * 1.44269504088896338700);
+                // c_B <= c_A: an entry below the cut at B is below it at A
+                const int cut32 = __float_as_int((float)(p.cut * (tabbed ? tab_rc[posB] : 1.0 / cB)));
+                int kaA[3], kaB[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const bool in = lane + 32 * i < kNS;
+                    kaA[i] = in ? (int)__ldg(p.kidx + (size_t)lamA * kNS + lane + 32 * i) : 0;
+                    kaB[i] = in ? (int)__ldg(p.kidx + (size_t)lamB * kNS + lane + 32 * i) : 0;
+                }
+                Z2 vf[40];
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) {
+                    float df[10], tf[10];
+                    bool dead = true;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int n = slot_e<NF>(j * 8 + n1, lane, 0);
+                        df[2 * j] = sD32[n];
+                        df[2 * j + 1] = sD32[kN + n];
+                        tf[2 * j] = sT32[n];
+                        tf[2 * j + 1] = sT32[kN + n];
+                        dead = dead & ((tf[2 * j] == 0.f) | (__float_as_int(df[2 * j]) >= cut32)) &
+                               ((tf[2 * j + 1] == 0.f) | (__float_as_int(df[2 * j + 1]) >= cut32));
+                    }
+                    if (__all_sync(0xffffffffu, dead)) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            vf[j * 8 + n1].x = F2(0.f, 0.f);
+                            vf[j * 8 + n1].y = F2(0.f, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            vf[j * 8 + n1].x = F2(ex2_approx(nA * df[2 * j]) * tf[2 * j], ex2_approx(nB * df[2 * j]) * tf[2 * j]);
+                            vf[j * 8 + n1].y = F2(ex2_approx(nA * df[2 * j + 1]) * tf[2 * j + 1],
+                                                  ex2_approx(nB * df[2 * j + 1]) * tf[2 * j + 1]);
+                        }
+                    }
+                }
+                warp_fft<kR3>(vf, xb, p.tw32, p.tw32 + G::TW1, lane);
+                float2* xf = reinterpret_cast<float2*>(xb);
+                // natural-order dump of one component (both wavelengths) per round; wavelength A reads
+                // the first halves at its own sampled frequencies, B the second halves at its own
+                float2 fa[3], fb[3], ga[3], gb[3];   // A: X[kA], X[-kA]; B likewise
+#pragma unroll
+                for (int cpt = 0; cpt < 2; ++cpt) {
+                    fft_dump<kR3>(vf, xf, lane, cpt);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float a = xf[nat_addr(kaA[i] % kNB)].x, am = xf[nat_addr(((kN - kaA[i]) % kN) % kNB)].x;
+                        const float b = xf[nat_addr(kaB[i] % kNB)].y, bm = xf[nat_addr(((kN - kaB[i]) % kN) % kNB)].y;
+                        if (cpt == 0) {
+                            fa[i].x = a; fb[i].x = am; ga[i].x = b; gb[i].x = bm;
+                        } else {
+                            fa[i].y = a; fb[i].y = am; ga[i].y = b; gb[i].y = bm;
+                        }
+                    }
+                    __syncwarp();
+                }
+                double2* outA = out_of(lamA);
+                double2* outB = out_of(lamB);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    store_rows(outA, i, make_double2((double)fa[i].x, (double)fa[i].y),
+                               make_double2((double)fb[i].x, (double)fb[i].y));
+                    if (two)
+                        store_rows(outB, i, make_double2((double)ga[i].x, (double)ga[i].y),
+                                   make_double2((double)gb[i].x, (double)gb[i].y));
+                }
+            } else {
+                const int pos = lb + (slot - npair);   // without the single-precision class lb = la, npair = 0
+                const int lam = lam_of(pos);
+                const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
+                double2* out = out_of(lam);
                 const double negc = -cl;
                 // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
                 const uint16_t* kx = p.kidx + (size_t)lam * kNS;
@@ -271,49 +371,6 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 const float negc2f = (float)(negc * 1.44269504088896338700);   // exp(-c D) = 2^(negc2f D)
                 const int cut32 = __float_as_int((float)(p.cut * rcl));
                 const int grade32 = __float_as_int((float)(p.grade * rcl));
-                if (f32_unit) {
-                    // ---- single-precision unit: every entry of both rows is below exp(-f32_min)
-                    // (default e^-25 = 1.4e-11) of the OTF peak, so a relative error of 1e-6 in this
-                    // unit's contribution is < 1e-17 of the peak: exp (MUFU ex2), the products and
-                    // the transform run in FP32, off the FP64 pipe, from the FP32 copies of D and T.
-                    float2 vf[40];
-#pragma unroll
-                    for (int n1 = 0; n1 < 8; ++n1) {
-                        float df[10], tf[10];
-                        bool dead = true;
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            const int n = slot_e<NF>(j * 8 + n1, lane, 0);
-                            df[2 * j] = sD32[n];
-                            df[2 * j + 1] = sD32[kN + n];
-                            tf[2 * j] = sT32[n];
-                            tf[2 * j + 1] = sT32[kN + n];
-                            dead = dead & ((tf[2 * j] == 0.f) | (__float_as_int(df[2 * j]) >= cut32)) &
-                                   ((tf[2 * j + 1] == 0.f) | (__float_as_int(df[2 * j + 1]) >= cut32));
-                        }
-                        if (__all_sync(0xffffffffu, dead)) {
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) vf[j * 8 + n1] = make_float2(0.f, 0.f);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 5; ++j)
-                                vf[j * 8 + n1] = make_float2(ex2_approx(negc2f * df[2 * j]) * tf[2 * j],
-                                                             ex2_approx(negc2f * df[2 * j + 1]) * tf[2 * j + 1]);
-                        }
-                    }
-                    warp_fft<kR3>(vf, xb, p.tw32, p.tw32 + G::TW1, lane);
-                    float2* xf = reinterpret_cast<float2*>(xb);
-                    fft_dump<kR3>(vf, xf, lane, 0);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const float2 a = xf[nat_addr(ka[i] % kNB)];
-                        const float2 b = xf[nat_addr(((kN - ka[i]) % kN) % kNB)];
-                        za[i] = make_double2((double)a.x, (double)a.y);
-                        zb[i] = make_double2((double)b.x, (double)b.y);
-                    }
-                    __syncwarp();
-                } else {
 #pragma unroll 1
                 for (int sub = 0; sub < NF; ++sub) {
                     double2 v[40];
@@ -430,16 +487,8 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         }
                     }
                 }
-                }
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int y = lane + 32 * i;
-                    if (y < kNS) {
-                        st_global_256(out + (size_t)y * kRows,
-                                      make_double2(0.5 * (za[i].x + zb[i].x), 0.5 * (za[i].y - zb[i].y)),
-                                      make_double2(0.5 * (za[i].y + zb[i].y), 0.5 * (zb[i].x - za[i].x)));
-                    }
-                }
+                for (int i = 0; i < 3; ++i) store_rows(out, i, za[i], zb[i]);
             }
         }
         // move on to the next round's first unit BEFORE its barrier: the items that lie wholly

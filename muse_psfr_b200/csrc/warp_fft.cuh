@@ -26,11 +26,16 @@
 // Every function is __host__ __device__ so that tools/host_check.cu can run the very
 // same code lane by lane on the CPU.
 //
-// The transform is templated on the complex type Z: double2 (the product path) or float2, which
-// the stage-B row kernel uses for row pairs whose every entry is below exp(-25) of the OTF peak
-// (psfr_hot.cu).  A float2 is one 8-byte shared-memory word, so the single-precision exchanges
-// move both components in ONE round through the same conflict-free layouts; its twiddles come
-// from a float2 copy of the tables (a double -> float conversion costs as much as four FMAs).
+// The transform is templated on the complex type Z: double2 (the product path), float2, or
+// Z2 = a complex number whose components are PACKED PAIRS of floats (F2: two independent
+// transforms, i.e. two wavelengths of the same row pair, in the f32x2 instructions of sm_100 -
+// FADD2 / FMUL2 / FFMA2 - at half the instruction count of two float2 transforms).  The stage-B
+// row kernel uses Z2 for row pairs whose every entry is below exp(-25) of the OTF peak
+// (psfr_hot.cu).  One exchange word is 8 bytes in every instantiation (a double, a float2, or
+// the F2 of one component), so all of them move through the same conflict-free layouts:
+// double2 and Z2 in two rounds (real parts, imaginary parts), float2 in one.  Single-precision
+// twiddles come from a float2 copy of the tables (a double -> float conversion costs as much
+// as four FMAs).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -52,6 +57,59 @@ struct ZTraits<float2> {
     using W = float2;   // both components in one 8-byte word, one round
     static constexpr int Rounds = 1;
 };
+// two independent single-precision values in one 64-bit register pair
+struct F2 {
+    float2 v;
+    PSFR_HD F2() {}
+    PSFR_HD F2(float a, float b) {
+        v.x = a;
+        v.y = b;
+    }
+    PSFR_HD explicit F2(double c) { v.x = v.y = (float)c; }   // constants, same in both halves
+};
+PSFR_HD F2 operator+(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    F2 r;
+    r.v = __fadd2_rn(a.v, b.v);
+    return r;
+#else
+    return F2(a.v.x + b.v.x, a.v.y + b.v.y);
+#endif
+}
+PSFR_HD F2 operator*(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    F2 r;
+    r.v = __fmul2_rn(a.v, b.v);
+    return r;
+#else
+    return F2(a.v.x * b.v.x, a.v.y * b.v.y);
+#endif
+}
+// a * b + c in one FFMA2
+PSFR_HD F2 sfma(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    F2 r;
+    r.v = __ffma2_rn(a.v, b.v, c.v);
+    return r;
+#else
+    return F2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
+#endif
+}
+// a - b = b * (-1) + a, exact, one FFMA2 (the packed add has no negated operand)
+PSFR_HD F2 operator-(F2 a, F2 b) { return sfma(b, F2(-1.f, -1.f), a); }
+PSFR_HD double sfma(double a, double b, double c) { return a * b + c; }
+PSFR_HD float sfma(float a, float b, float c) { return a * b + c; }
+
+struct Z2 {
+    F2 x, y;
+};
+template <>
+struct ZTraits<Z2> {
+    using S = F2;
+    using W = float2;   // the F2 of one component per round
+    static constexpr int Rounds = 2;
+};
+
 template <class Z>
 PSFR_HD Z mkz(typename ZTraits<Z>::S x, typename ZTraits<Z>::S y) {
     Z r;
@@ -67,46 +125,55 @@ PSFR_HD Z ztw(const TW& w) {
     return mkz<Z>((S)w.x, (S)w.y);
 }
 
+template <>
+PSFR_HD Z2 ztw<Z2, float2>(const float2& w) {
+    Z2 r;
+    r.x = F2(w.x, w.x);
+    r.y = F2(w.y, w.y);
+    return r;
+}
+
 template <class Z>
 PSFR_HD Z cadd(Z a, Z b) { return mkz<Z>(a.x + b.x, a.y + b.y); }
 template <class Z>
 PSFR_HD Z csub(Z a, Z b) { return mkz<Z>(a.x - b.x, a.y - b.y); }
 template <class Z>
 PSFR_HD Z cmul(Z a, Z b) { return mkz<Z>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-// a * i and a * (-i)
+template <>
+PSFR_HD Z2 cmul<Z2>(Z2 a, Z2 b) { return mkz<Z2>(a.x * b.x - a.y * b.y, sfma(a.y, b.x, a.x * b.y)); }
+// a + i b and a - i b (no negation: the packed type has none for free)
 template <class Z>
-PSFR_HD Z cmuli(Z a) { return mkz<Z>(-a.y, a.x); }
+PSFR_HD Z caddi(Z a, Z b) { return mkz<Z>(a.x - b.y, a.y + b.x); }
 template <class Z>
-PSFR_HD Z cmulni(Z a) { return mkz<Z>(a.y, -a.x); }
+PSFR_HD Z csubi(Z a, Z b) { return mkz<Z>(a.x + b.y, a.y - b.x); }
 
 // ---- small DFTs, sign +i:  X[k] = sum_n x[n] exp(+2 pi i n k / R) -------------------
 template <class Z>
 PSFR_HD void dft4(Z& x0, Z& x1, Z& x2, Z& x3) {
-    Z a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = cmuli(csub(x1, x3));
+    Z a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = csub(x1, x3);
     x0 = cadd(a, c);
     x2 = csub(a, c);
-    x1 = cadd(b, d);
-    x3 = csub(b, d);
+    x1 = caddi(b, d);
+    x3 = csubi(b, d);
 }
 
 template <class Z>
 PSFR_HD void dft8(Z* x) {
     using S = typename ZTraits<Z>::S;
-    const S h = (S)0.70710678118654752440;
+    const S h = (S)0.70710678118654752440, mh = (S)-0.70710678118654752440;
     Z e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
     Z o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
     dft4(e0, e1, e2, e3);
     dft4(o0, o1, o2, o3);
     // o_k *= w8^k, w8 = exp(+i pi/4)
     o1 = mkz<Z>(h * (o1.x - o1.y), h * (o1.x + o1.y));
-    o2 = cmuli(o2);
-    o3 = mkz<Z>(-h * (o3.x + o3.y), h * (o3.x - o3.y));
+    o3 = mkz<Z>(mh * (o3.x + o3.y), h * (o3.x - o3.y));
     x[0] = cadd(e0, o0);
     x[4] = csub(e0, o0);
     x[1] = cadd(e1, o1);
     x[5] = csub(e1, o1);
-    x[2] = cadd(e2, o2);
-    x[6] = csub(e2, o2);
+    x[2] = caddi(e2, o2);   // o2 * w8^2 = i o2
+    x[6] = csubi(e2, o2);
     x[3] = cadd(e3, o3);
     x[7] = csub(e3, o3);
 }
@@ -118,16 +185,17 @@ PSFR_HD void dft5(Z& x0, Z& x1, Z& x2, Z& x3, Z& x4) {
     const S c2 = (S)-0.80901699437494742410;  // cos(4pi/5)
     const S s1 = (S)0.95105651629515357212;   // sin(2pi/5)
     const S s2 = (S)0.58778525229247312917;   // sin(4pi/5)
+    const S ms1 = (S)-0.95105651629515357212;
     Z t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-    Z a1 = mkz<Z>(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-    Z a2 = mkz<Z>(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-    Z b1 = mkz<Z>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    Z b2 = mkz<Z>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    Z a1 = mkz<Z>(sfma(c2, t2.x, sfma(c1, t1.x, x0.x)), sfma(c2, t2.y, sfma(c1, t1.y, x0.y)));
+    Z a2 = mkz<Z>(sfma(c1, t2.x, sfma(c2, t1.x, x0.x)), sfma(c1, t2.y, sfma(c2, t1.y, x0.y)));
+    Z b1 = mkz<Z>(sfma(s1, t3.x, s2 * t4.x), sfma(s1, t3.y, s2 * t4.y));
+    Z b2 = mkz<Z>(sfma(ms1, t4.x, s2 * t3.x), sfma(ms1, t4.y, s2 * t3.y));
     x0 = mkz<Z>(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
-    x1 = cadd(a1, cmuli(b1));
-    x4 = csub(a1, cmuli(b1));
-    x2 = cadd(a2, cmuli(b2));
-    x3 = csub(a2, cmuli(b2));
+    x1 = caddi(a1, b1);
+    x4 = csubi(a1, b1);
+    x2 = caddi(a2, b2);
+    x3 = csubi(a2, b2);
 }
 
 template <int RA, class Z>
@@ -200,6 +268,10 @@ PSFR_HD void word_set(double2& a, int c, double v) {
 }
 PSFR_HD float2 word_get(const float2& a, int) { return a; }
 PSFR_HD void word_set(float2& a, int, float2 v) { a = v; }
+PSFR_HD float2 word_get(const Z2& a, int c) { return c ? a.y.v : a.x.v; }
+PSFR_HD void word_set(Z2& a, int c, float2 v) {
+    if (c) a.y.v = v; else a.x.v = v;
+}
 
 template <int R3, class Z, class TW>
 PSFR_HD void fft_pass1(Z* v, const TW* tw1, int t) {

@@ -61,6 +61,65 @@ int check(double tol) {
     return maxerr / maxref < tol ? 0 : 1;
 }
 
+// Z2: two independent single-precision transforms packed into one (f32x2 lanes on the device,
+// emulated with scalar floats on the host); both halves are checked against the direct DFT.
+template <int R3>
+int check_packed(double tol) {
+    using G = FftGeom<R3>;
+    const int N = G::N;
+    std::vector<double2> tw1d, tw2d;
+    build_twiddles<R3>(tw1d, tw2d);
+    std::vector<float2> tw1(tw1d.size()), tw2(tw2d.size());
+    for (size_t i = 0; i < tw1d.size(); ++i) tw1[i] = make_float2((float)tw1d[i].x, (float)tw1d[i].y);
+    for (size_t i = 0; i < tw2d.size(); ++i) tw2[i] = make_float2((float)tw2d[i].x, (float)tw2d[i].y);
+    std::vector<Z2> x(N);
+    srand(2);
+    auto rnd = [] { return (float)(rand() / (double)RAND_MAX - 0.5); };
+    for (auto& z : x) {
+        z.x = F2(rnd(), rnd());
+        z.y = F2(rnd(), rnd());
+    }
+    std::vector<std::vector<Z2>> v(32, std::vector<Z2>(40));
+    std::vector<float2> sm(G::XBUF);
+    for (int t = 0; t < 32; ++t)
+        for (int j = 0; j < 5; ++j)
+            for (int n1 = 0; n1 < 8; ++n1) v[t][j * 8 + n1] = x[n1 * (N / 8) + t + 32 * j];
+    for (int t = 0; t < 32; ++t) fft_pass1<R3>(v[t].data(), tw1.data(), t);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_x1_store<R3>(v[t].data(), sm.data(), t, c);
+        for (int t = 0; t < 32; ++t) fft_x1_load<R3>(v[t].data(), sm.data(), t, c);
+    }
+    for (int t = 0; t < 32; ++t) fft_pass2<R3>(v[t].data(), tw2.data(), t);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_x2_store<R3>(v[t].data(), sm.data(), t, c);
+        for (int t = 0; t < 32; ++t) fft_x2_load<R3>(v[t].data(), sm.data(), t, c);
+    }
+    for (int t = 0; t < 32; ++t) fft_pass3<R3>(v[t].data());
+    std::vector<Z2> X(N);
+    for (int c = 0; c < 2; ++c) {
+        for (int t = 0; t < 32; ++t) fft_dump<R3>(v[t].data(), sm.data(), t, c);
+        for (int k = 0; k < N; ++k) word_set(X[k], c, sm[nat_addr(k)]);
+    }
+    double maxerr = 0, maxref = 0;
+    for (int half = 0; half < 2; ++half)
+        for (int k = 0; k < N; k += 7) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < N; ++n) {
+                double2 w = unit_root((long long)n * k, N);
+                const double xr = half ? x[n].x.v.y : x[n].x.v.x, xi = half ? x[n].y.v.y : x[n].y.v.x;
+                sr += (long double)xr * w.x - (long double)xi * w.y;
+                si += (long double)xr * w.y + (long double)xi * w.x;
+            }
+            const double gr = half ? X[k].x.v.y : X[k].x.v.x, gi = half ? X[k].y.v.y : X[k].y.v.x;
+            double e = fabs((double)(sr - gr)) + fabs((double)(si - gi));
+            if (e > maxerr) maxerr = e;
+            double r = fabs((double)sr) + fabs((double)si);
+            if (r > maxref) maxref = r;
+        }
+    printf("N=%d packed float pair max err %.3e (ref scale %.3e) rel %.3e\n", N, maxerr, maxref, maxerr / maxref);
+    return maxerr / maxref < tol ? 0 : 1;
+}
+
 int main() {
     // small DFT sanity: dft_r3 for 5,10,20,40
     int bad = 0;
@@ -88,5 +147,6 @@ int main() {
     }
     bad |= check<20, double2>(1e-14);
     bad |= check<20, float2>(2e-6);
+    bad |= check_packed<20>(2e-6);
     return bad;
 }
