@@ -143,6 +143,9 @@ def run_gpu(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     psfrec.set_device(local)
