@@ -56,14 +56,9 @@ __device__ __forceinline__ double f2d_bits(float f) {
     return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
 
-// sign-agnostic test for zero and "x <= -cut" on the integer pipe.  For x < 0 the high word
-// grows with |x|, so x <= -cut <=> hi(x) >= hi(-cut) as unsigned (up to the low word of cut,
-// which is irrelevant for a threshold); non-negative x has the sign bit clear and never passes.
+// sign-agnostic test for zero on the integer pipe
 __device__ __forceinline__ bool is_zero_bits(double t) {
     return ((__double2hiint(t) << 1) | __double2loint(t)) == 0;
-}
-__device__ __forceinline__ bool below_cut(double x, unsigned cut_hi) {
-    return (unsigned)__double2hiint(x) >= cut_hi;
 }
 
 }  // namespace psfr

@@ -5,13 +5,15 @@
 // result (bilinear resampling to 40 x 40).  Here:
 //
 //  * hot_rows_kernel  - persistent, one CTA per SM.  Row pairs of the structure function D
-//    (and of the telescope OTF) stream into a shared-memory ring with TMA bulk copies
-//    (cp.async.bulk + mbarrier complete_tx), issued by whichever warp releases a stage
-//    last; eight warps each take one wavelength at a time: OTF rows = exp(-c_lambda D) * T
-//    evaluated straight from shared memory into registers, one 1280-point warp FFT for the two packed real rows,
-//    and only the 80 sampled frequencies (+ mirrors) are untangled and written, as one
-//    32-byte sector per frequency.  D is read from HBM/L2 once per row pair for ALL
-//    wavelengths; the N x N OTF and PSF grids never exist in memory.
+//    and of the telescope OTF (FP64 and FP32 copies) stream into a shared-memory ring with TMA
+//    bulk copies (cp.async.bulk + mbarrier complete_tx), issued by whichever warp releases a
+//    stage last.  A unit = one row pair at one wavelength: OTF rows = exp(-c_lambda D) * T
+//    evaluated straight from shared memory into registers (graded precision),
+//    one 1280-point warp FFT for the two packed real rows, and only the 80 sampled frequencies
+//    (+ mirrors) are untangled and written, as one 32-byte sector per frequency.  The eight
+//    warps run their units in lockstep rounds so that they share instruction fetches (3.10).
+//    D is read from HBM/L2 once per row pair for ALL wavelengths; the N x N OTF and PSF grids
+//    never exist in memory.
 //  * hot_cols pass    - 40 Hermitian column-pair transforms per PSF (summing the field
 //    directions of a draw before the transform: the mean over directions, psfrec.py:674,
 //    commutes with the linear transform), keeping the 80 sampled outputs -> 80x80 samples.
@@ -53,7 +55,6 @@ struct HotParams {
     const double* D;       // [nplanes][kRows][N]
     const double* T;       // [kRows][N]
     double2* Y;            // [nplanes][nlam][kNS][kRows]
-    const double* clam;    // [nlam]
     const uint16_t* kidx;  // [nlam][kNS]
     const double2* wsamp;  // [nlam][2][kNS] NF = 2: w_N^k of the sampled outputs and of their mirrors
     const double* dmin;    // [nplanes][kRows] smallest D of each row (StoreDphi)
@@ -85,7 +86,6 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     volatile int* la_of = item_of + kStages;                  // per-stage: sorted positions [0, la) are dead,
     volatile int* lb_of = la_of + kStages;                    //   [la, lb) single precision, [lb, nlam) FP64
     volatile int* ns_of = lb_of + kStages;                    // per-stage number of stream slots of the item
-    volatile double* dmin_of = reinterpret_cast<volatile double*>(smem_raw + 64);   // per-stage min(D) of the row pair
     static_assert(kStages == 2, "the 128-byte header is laid out for two stages");
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
@@ -114,7 +114,6 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             item_of[s] = item;
             const double dm = fmin(__ldg(p.dmin + (size_t)plane * kRows + 2 * rp),
                                    __ldg(p.dmin + (size_t)plane * kRows + 2 * rp + 1));
-            dmin_of[s] = dm;   // travels with the item id
             // Classes of the item's nlam units, by binary search on the descending c_lambda:
             // c * min(D) > cut -> dead (the transform of both rows is zero), >= f32_min ->
             // single precision, else FP64.  Both predicates are monotone along the sorted order.
@@ -641,7 +640,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     using C = HotCfg<NF>;
     if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_lam, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_dphi32,
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_dphi32,
                 c->d_otf32, c->d_tw32, c->d_csort, c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;

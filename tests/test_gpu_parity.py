@@ -216,6 +216,24 @@ def test_psf_muse_nine_directions(psfrec, golden):
         assert_image_close(got[i], g['psf_muse'][i])
 
 
+def test_psf_muse_wavelength_order_and_count(psfrec, psd1):
+    """The row kernel works through the wavelengths in sorted order and stages their scalars in
+    shared memory up to 64 of them: an unsorted list, and a list longer than 64, must give the
+    same planes as one-at-a-time calls."""
+    rng = np.random.default_rng(7)
+    lam = rng.permutation(np.linspace(495, 925, 70))
+    cube = psfrec.psf_muse(psd1[0], lam)
+    assert cube.shape == (70, 40, 40)
+    for k in (0, 1, 33, 69):
+        one = psfrec.psf_muse(psd1[0], lam[[k]])[0]
+        assert rel_to_peak(cube[k], one) < 1e-13
+    sub = psfrec.psf_muse(psd1[0], lam[:9])
+    assert rel_to_peak(cube[:9], sub) < 1e-13
+    ref = orc.psf_muse(psd1[0], lam[[5, 40]])
+    assert_image_close(cube[5], ref[0])
+    assert_image_close(cube[40], ref[1])
+
+
 def test_psf_muse_pruned_equals_full_grid(psfrec, psd1):
     """The pruned 80x80-sample transform against the full-grid PSF resampled on the host."""
     from scipy.interpolate import interpn
