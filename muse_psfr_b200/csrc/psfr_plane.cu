@@ -86,6 +86,10 @@ resample_kernel(const double* __restrict__ samp, const double* __restrict__ frac
 // end with bit-identical sums, so the 5x5 solve and the LM control flow run redundantly and
 // uniformly in every lane) - no block-level synchronisation at all.
 constexpr int kFitWarps = 4;
+// resident CTAs per SM the fitter is compiled for (register budget 65536 / (128 * this))
+#ifndef PSFR_FIT_MINBLOCKS
+#define PSFR_FIT_MINBLOCKS 4
+#endif
 constexpr int kNP = 5;
 constexpr int kNSUM = 21;  // 15 (J^T J upper) + 5 (J^T r) + 1 (cost)
 
@@ -284,7 +288,7 @@ __device__ __forceinline__ void lm_solve(const double* __restrict__ img, int npx
     }
 }
 
-__global__ void __launch_bounds__(kFitWarps * 32)
+__global__ void __launch_bounds__(kFitWarps * 32, PSFR_FIT_MINBLOCKS)
 fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __restrict__ out,
            int* __restrict__ next_image) {
     extern __shared__ double sm[];
