@@ -117,6 +117,17 @@ __global__ void ao_zone_kernel(PsdParams p) {
     p.ao[((size_t)plane * kAO + i) * kAO + j] = dsp;
 }
 
+// psd_fit (psfrec.py:616-626) at quadrant cell (a, b), unscaled.  Evaluated with the smaller
+// index first, so that fit(a, b) and fit(b, a) are the same bits whatever the compiler contracts
+// into an FMA: psd_quad_kernel evaluates one triangle and mirrors it.
+__device__ __forceinline__ double fit_cell(int a, int b, int kN, double fitc, double inv_l0sq) {
+    const double L = 16.0, fc = 1 / (2 * (8.0 / 24.0));
+    const int lo = min(a, b), hi = max(a, b);
+    const double ua = (lo - (kN - 1) / 2.0) / L, ub = (hi - (kN - 1) / 2.0) / L;
+    const double f = sqrt(ua * ua + ub * ub);
+    return f >= fc ? fitc * pow_m11_6(f * f + inv_l0sq) : 0.0;
+}
+
 __global__ void psd_fill_kernel(const double* __restrict__ draws, const double* __restrict__ ao,
                                 double* __restrict__ psd, int ndir, double scale2, int kN) {
     // one thread per quadrant cell (a, b), a, b in [0, N/2): fit(a,b) = fit(N-1-a, b) = ...
@@ -126,12 +137,8 @@ __global__ void psd_fill_kernel(const double* __restrict__ draws, const double* 
     const int plane = blockIdx.z;
     if (b >= kNH) return;
     const double* dr = draws + (size_t)(plane / ndir) * PSFR_DRAW_NPAR;
-    const double L = 16.0, fc = 1 / (2 * (8.0 / 24.0));
     const double L0 = dr[PSFR_DRAW_L0];
-    const double ua = (a - (kN - 1) / 2.0) / L, ub = (b - (kN - 1) / 2.0) / L;
-    const double f = sqrt(ua * ua + ub * ub);
-    double fit = 0.0;
-    if (f >= fc) fit = dr[PSFR_DRAW_FITC] * pow_m11_6(f * f + (1 / L0) * (1 / L0));
+    const double fit = fit_cell(a, b, kN, dr[PSFR_DRAW_FITC], (1 / L0) * (1 / L0));
     double* base = psd + (size_t)plane * kN * kN;
     const int lo = kNH - kAO / 2, hi = kNH + kAO / 2;
     const double* z = ao + (size_t)plane * kAO * kAO;
@@ -150,20 +157,35 @@ __global__ void psd_fill_kernel(const double* __restrict__ draws, const double* 
 // materialises the N x N PSD: LoadEvenRowsQuad (psfr_passes.cu) applies the AO-zone max() and the
 // nm^2 scale with the same operations in the same order as psd_fill_kernel, so both paths give
 // bit-identical structure functions.
-__global__ void psd_quad_kernel(const double* __restrict__ draws, double* __restrict__ q, int kN) {
-    const int kNH = kN / 2;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int a = blockIdx.y;
-    const int draw = blockIdx.z;
-    if (b >= kNH) return;
-    const double* dr = draws + (size_t)draw * PSFR_DRAW_NPAR;
-    const double L = 16.0, fc = 1 / (2 * (8.0 / 24.0));
-    const double L0 = dr[PSFR_DRAW_L0];
-    const double ua = (a - (kN - 1) / 2.0) / L, ub = (b - (kN - 1) / 2.0) / L;
-    const double f = sqrt(ua * ua + ub * ub);
-    double fit = 0.0;
-    if (f >= fc) fit = dr[PSFR_DRAW_FITC] * pow_m11_6(f * f + (1 / L0) * (1 / L0));
-    q[((size_t)draw * kNH + a) * kNH + b] = fit;
+// The fit depends on (a, b) through ua^2 + ub^2 only: one 32 x 32 tile per unordered tile pair
+// (ta <= tb) is evaluated (x^(-11/6) is what the kernel costs) and written twice, straight and
+// transposed through shared memory, both coalesced.
+__global__ void __launch_bounds__(256)
+psd_quad_kernel(const double* __restrict__ draws, double* __restrict__ q, int kN) {
+    __shared__ double tile[32][33];
+    const int kNH = kN / 2, nt = kNH / 32;
+    // blockIdx.x enumerates the pairs (ta, tb), ta <= tb, row by row
+    int ta = 0, rest = blockIdx.x;
+    while (rest >= nt - ta) {
+        rest -= nt - ta;
+        ++ta;
+    }
+    const int tb = ta + rest;
+    const double* dr = draws + (size_t)blockIdx.y * PSFR_DRAW_NPAR;
+    const double L0 = dr[PSFR_DRAW_L0], fitc = dr[PSFR_DRAW_FITC], inv = (1 / L0) * (1 / L0);
+    double* base = q + (size_t)blockIdx.y * kNH * kNH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int a = ta * 32 + r, b = tb * 32 + tx;
+        const double v = fit_cell(a, b, kN, fitc, inv);
+        tile[r][tx] = v;
+        base[(size_t)a * kNH + b] = v;
+    }
+    if (ta == tb) return;   // uniform per block: a diagonal tile holds both of its triangles
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) base[(size_t)(tb * 32 + r) * kNH + ta * 32 + tx] = tile[tx][r];
 }
 
 int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s, bool full) {
@@ -173,8 +195,9 @@ int run_psd(Ctx* c, int ndraw, int ndir, int ngs, cudaStream_t s, bool full) {
     ao_zone_kernel<<<g1, 128, 0, s>>>(p);
     PSFR_LAUNCH_CHECK(c);
     if (!full) {
-        dim3 gq((c->NH + 127) / 128, c->NH, ndraw);          // one quadrant per DRAW
-        psd_quad_kernel<<<gq, 128, 0, s>>>(c->d_draws, c->d_psdq, c->N);
+        const int nt = c->NH / 32;                           // NH = 640 or 1280
+        dim3 gq(nt * (nt + 1) / 2, ndraw);                   // one quadrant per DRAW, one triangle of tiles
+        psd_quad_kernel<<<gq, 256, 0, s>>>(c->d_draws, c->d_psdq, c->N);
         PSFR_LAUNCH_CHECK(c);
         c->planes_loaded = 0;
         c->planes_struct = 0;
