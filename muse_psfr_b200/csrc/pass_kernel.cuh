@@ -77,27 +77,39 @@ pass_kernel(Loader ld, Storer st, int nfft, const double2* __restrict__ g_tw, co
 }
 
 // Tile-staged variant (dim 1280): the input of a line is one contiguous block of global memory
-// (`src.block(f, &bytes)`); every warp owns a private shared-memory tile that a TMA bulk copy
-// fills while the warp transforms the previous line - the tile is dead as soon as `build` has
-// turned it into the 40 register values - so the pass streams its input at HBM speed instead of
-// waiting on dependent per-lane loads.  Lines are dealt to the warps in a fixed stride.
-template <int WARPS, int TILE_BYTES>
+// (`src.block(f, &bytes)`) that a TMA bulk copy brings into a warp-private shared-memory tile, so
+// the pass streams its input at HBM speed instead of waiting on dependent per-lane loads.  Lines
+// are dealt to the warps in a fixed stride.  The tile is dead as soon as `build` has turned it
+// into the 40 register values; two ways to use that:
+//   OVERLAP = true : the next tile is fetched while the warp transforms the current line; the
+//                    natural-order dump needs its own two regions (re, im) -> 5 warps fit;
+//   OVERLAP = false: the dead tile doubles as the imaginary half of the dump and the next tile
+//                    is fetched after the store -> 8 (6) warps fit.  These kernels run one
+//                    long dependent instruction stream per warp, so warps per scheduler count
+//                    for more than the ~1.5 us of TMA latency per line that they now hide for
+//                    each other.
+template <int WARPS, int TILE_BYTES, bool OVERLAP>
 constexpr size_t tiled_pass_smem() {
-    return 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) + (size_t)WARPS * (TILE_BYTES + 2 * G::XBUF * sizeof(double));
+    return 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
+           (size_t)WARPS * (TILE_BYTES + (OVERLAP ? 2 : 1) * G::XBUF * sizeof(double));
 }
 
-template <int WARPS, int TILE_BYTES, class Src, class Storer>
+template <int WARPS, int TILE_BYTES, bool OVERLAP, class Src, class Storer>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 tiled_pass_kernel(Src src, Storer st, int nfft, const double2* __restrict__ g_tw) {
     static_assert(TILE_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+    static_assert(OVERLAP || TILE_BYTES >= G::XBUF * sizeof(double), "the tile must hold one dump region");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* tiles = reinterpret_cast<unsigned char*>(tw2 + G::TW2);
-    unsigned char* tile = tiles + (size_t)warp * TILE_BYTES;
-    double* xb = reinterpret_cast<double*>(tiles + (size_t)WARPS * TILE_BYTES) + (size_t)warp * 2 * G::XBUF;
+    // per warp: [re dump = exchange scratch : XBUF][im dump : XBUF (OVERLAP only)][tile]; the storers
+    // read im at xb + XBUF, which is the tile itself when it doubles as the im dump
+    constexpr size_t kWarpBytes = TILE_BYTES + (OVERLAP ? 2 : 1) * G::XBUF * sizeof(double);
+    unsigned char* mine = reinterpret_cast<unsigned char*>(tw2 + G::TW2) + (size_t)warp * kWarpBytes;
+    double* xb = reinterpret_cast<double*>(mine);
+    unsigned char* tile = mine + (OVERLAP ? 2 : 1) * G::XBUF * sizeof(double);
     uint64_t* bar = bars + warp;
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
     if (lane == 0) mbar_init(bar, 1);
@@ -123,25 +135,26 @@ tiled_pass_kernel(Src src, Storer st, int nfft, const double2* __restrict__ g_tw
         phase ^= 1;
         src.build(f, lane, tile, v);
         __syncwarp();
-        if (f + nw < nfft) fetch(f + nw);
-        warp_fft<kR3>(v, xb + G::XBUF, tw1, tw2, lane);
+        if (OVERLAP && f + nw < nfft) fetch(f + nw);
+        warp_fft<kR3>(v, xb, tw1, tw2, lane);
         __syncwarp();
         fft_dump<kR3>(v, xb, lane, 0);
         fft_dump<kR3>(v, xb + G::XBUF, lane, 1);
         __syncwarp();
         st(f, lane, xb);
         __syncwarp();
+        if (!OVERLAP && f + nw < nfft) fetch(f + nw);
     }
 }
 
-template <int WARPS, int TILE_BYTES, class Src, class Storer>
+template <int WARPS, int TILE_BYTES, bool OVERLAP, class Src, class Storer>
 static int launch_tiled_pass(Ctx* c, Src src, Storer st, int nfft, cudaStream_t s) {
-    constexpr size_t smem = tiled_pass_smem<WARPS, TILE_BYTES>();
+    constexpr size_t smem = tiled_pass_smem<WARPS, TILE_BYTES, OVERLAP>();
     static_assert(smem <= 232448, "tiled pass shared memory exceeds the 227 KB per-CTA limit");
-    if (int rc = ensure_dynamic_smem(c, tiled_pass_kernel<WARPS, TILE_BYTES, Src, Storer>, smem)) return rc;
+    if (int rc = ensure_dynamic_smem(c, tiled_pass_kernel<WARPS, TILE_BYTES, OVERLAP, Src, Storer>, smem)) return rc;
     int grid = (nfft + WARPS - 1) / WARPS;
     if (grid > c->sm_count) grid = c->sm_count;
-    tiled_pass_kernel<WARPS, TILE_BYTES, Src, Storer><<<grid, WARPS * 32, smem, s>>>(src, st, nfft, c->d_tw);
+    tiled_pass_kernel<WARPS, TILE_BYTES, OVERLAP, Src, Storer><<<grid, WARPS * 32, smem, s>>>(src, st, nfft, c->d_tw);
     PSFR_LAUNCH_CHECK(c);
     return PSFR_OK;
 }

@@ -11,6 +11,17 @@
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 
+// warps per CTA of the two tile-staged stage-A passes and whether they overlap the next tile's
+// load with the transform (pass_kernel.cuh): row pass 8 warps without overlap, column pass 6
+#ifndef PSFR_PASS1_WARPS
+#define PSFR_PASS1_WARPS 8
+#define PSFR_PASS1_OVERLAP false
+#endif
+#ifndef PSFR_PASS2_WARPS
+#define PSFR_PASS2_WARPS 6
+#define PSFR_PASS2_OVERLAP false
+#endif
+
 namespace psfr {
 
 // ------------------------------------------------------------------ loaders
@@ -392,7 +403,7 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_q
     int rc;
     if constexpr (NF == 1) {
         if (from_quadrant)
-            rc = launch_tiled_pass<5, SrcEvenRowsQuad::kTileBytes>(c, SrcEvenRowsQuad{c->d_psdq, c->d_ao, ndir, k * k},
+            rc = launch_tiled_pass<PSFR_PASS1_WARPS, SrcEvenRowsQuad::kTileBytes, PSFR_PASS1_OVERLAP>(c, SrcEvenRowsQuad{c->d_psdq, c->d_ao, ndir, k * k},
                                                                    StoreTransposedPair<1>{c->d_bt, D::Pairs},
                                                                    nplanes * D::Pairs, s);
         else
@@ -417,7 +428,7 @@ static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_q
                          StoreCentre<NF>{centre, scale}, nplanes, s);
     if (rc) return rc;
     if constexpr (NF == 1)
-        rc = launch_tiled_pass<5, SrcHermitianPair::kTileBytes>(c, SrcHermitianPair{c->d_bt, D::Pairs, D::NH},
+        rc = launch_tiled_pass<PSFR_PASS2_WARPS, SrcHermitianPair::kTileBytes, PSFR_PASS2_OVERLAP>(c, SrcHermitianPair{c->d_bt, D::Pairs, D::NH},
                                                                 StoreDphi<1>{c->d_dphi, centre, c->d_dmin, scale, c->d_dphi32},
                                                                 nplanes * D::Pairs, s);
     else
