@@ -508,12 +508,20 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
 // streams Y at HBM speed instead of waiting on 80 dependent 16-byte loads per lane.
 template <int NF>
 struct ColCfg {
-    static constexpr int Warps = NF == 1 ? 6 : 4;
+    // dim 1280: the tile is dead once its values sit in registers, so it doubles as the exchange
+    // buffer of the transform and the next line is fetched after the gather: 8 warps fit instead
+    // of 6 (these kernels are one long dependent instruction stream per warp - warps per
+    // scheduler count for more than the load latency the warps now hide for each other).
+    // dim 2560 keeps a separate exchange buffer and fetches ahead (4 warps either way).
+    static constexpr bool SharedTile = NF == 1;
+    static constexpr int Warps = NF == 1 ? 8 : 4;
     static constexpr int TileElems = 2 * Dim<NF>::Rows;                 // double2 per tile
     static constexpr uint32_t TileBytes = TileElems * sizeof(double2);
+    static constexpr size_t XbufBytes = SharedTile ? 0 : G::XBUF * sizeof(double);
     static constexpr size_t Smem = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) +
-                                   (size_t)Warps * (TileBytes + G::XBUF * sizeof(double));
+                                   (size_t)Warps * (TileBytes + XbufBytes);
     static_assert(TileBytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+    static_assert(!SharedTile || TileBytes >= G::XBUF * sizeof(double), "the tile must hold the exchange buffer");
     static_assert(Smem <= 232448, "column kernel shared memory exceeds the 227 KB per-CTA limit");
 };
 
@@ -537,7 +545,9 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
     double2* tw2 = tw1 + G::TW1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2* tile = tw2 + G::TW2 + (size_t)warp * C::TileElems;
-    double* xb = reinterpret_cast<double*>(tw2 + G::TW2 + (size_t)C::Warps * C::TileElems) + (size_t)warp * G::XBUF;
+    double* xb = C::SharedTile ? reinterpret_cast<double*>(tile)
+                               : reinterpret_cast<double*>(tw2 + G::TW2 + (size_t)C::Warps * C::TileElems) +
+                                     (size_t)warp * G::XBUF;
     uint64_t* bar = bars + warp;
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
@@ -596,10 +606,11 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
                     }
                 }
                 __syncwarp();
-                // the tile is dead: prefetch the next one of this warp's sequence
+                // the tile is dead: prefetch the next one of this warp's sequence (unless the
+                // transform is about to use the tile as its exchange buffer)
                 if (d + 1 < p.ndir) fetch(f, d + 1);
                 else if (sub + 1 < NF) fetch(f, 0);
-                else if (f + nw < p.nlines) fetch(f + nw, 0);
+                else if (!C::SharedTile && f + nw < p.nlines) fetch(f + nw, 0);
             }
             warp_fft<kR3>(v, xb, tw1, tw2, lane);
             double2 fz[3];
@@ -621,6 +632,7 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
                     if (lane + 32 * i < kNS) z[i] = cadd(z[i], cmul(fz[i], __ldg(ws + lane + 32 * i)));
             }
         }
+        if (C::SharedTile && f + nw < p.nlines) fetch(f + nw, 0);   // the gathers above are done (__syncwarp)
         const int k1 = __ldg(kx + 2 * m), k2 = __ldg(kx + 2 * m + 1);
         double* o = p.S + ((size_t)img * kNS + 2 * m) * kNS;
 #pragma unroll
