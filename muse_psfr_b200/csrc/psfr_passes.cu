@@ -249,7 +249,9 @@ struct StoreTransposedPair {
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / npair, rp = f % npair;
         double2* out = Bt + (size_t)plane * D::N * D::Rows + 2 * rp;
-#pragma unroll 4
+        // unrolled far enough that a store's data registers are not rewritten while it still
+        // sits in the store queue (ncu: long-scoreboard stalls on the first DADD of a trip)
+#pragma unroll 10
         for (int i = 0; i < 40 * NF; ++i) {
             const int y = lane + 32 * i;
             const double2 za = nat_get<NF>(xb, y), zb = nat_get<NF>(xb, (D::N - y) % D::N);
