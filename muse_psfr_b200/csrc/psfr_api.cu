@@ -96,6 +96,13 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_lam, cl.data(), nlam * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_frac, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kidx, kx.data(), kx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    // where the row kernel finds X[k] and X[-k] in its natural-order dump (per 1280-point sub-transform)
+    std::vector<ushort2> ka(kx.size());
+    for (size_t i = 0; i < kx.size(); ++i) {
+        const int k = kx[i], km = (kN - k) % kN;
+        ka[i] = make_ushort2((unsigned short)nat_addr(k % kNB), (unsigned short)nat_addr(km % kNB));
+    }
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_kaddr, ka.data(), ka.size() * sizeof(ushort2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));   // the host vectors go out of scope
     return PSFR_OK;
 }
@@ -176,7 +183,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
-    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_csort); cudaFree(c->d_lorder);
+    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -267,6 +274,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_csort, LM));
     CK(dev_alloc(c, &c->d_lorder, LM));
     CK(dev_alloc(c, &c->d_kidx, LM * kNS));
+    CK(dev_alloc(c, &c->d_kaddr, LM * kNS));
     CK(dev_alloc(c, &c->d_frac, LM * kPSF));
     CK(dev_alloc(c, &c->d_kern_tt, P * kKW * kKW));
     CK(dev_alloc(c, &c->d_kern_mu, LM * kKW * kKW));

@@ -55,7 +55,7 @@ struct HotParams {
     const double* D;       // [nplanes][kRows][N]
     const double* T;       // [kRows][N]
     double2* Y;            // [nplanes][nlam][kNS][kRows]
-    const uint16_t* kidx;  // [nlam][kNS]
+    const ushort2* kaddr;  // [nlam][kNS] where X[k], X[-k] of the sampled frequencies sit in the natural-order dump
     const double2* wsamp;  // [nlam][2][kNS] NF = 2: w_N^k of the sampled outputs and of their mirrors
     const double* dmin;    // [nplanes][kRows] smallest D of each row (StoreDphi)
     const float* D32;      // single-precision copies of D and T (dim 1280)
@@ -284,12 +284,12 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 const float nB = (float)(-cB * 1.44269504088896338700);
                 // c_B <= c_A: an entry below the cut at B is below it at A
                 const int cut32 = __float_as_int((float)(p.cut * (tabbed ? tab_rc[posB] : 1.0 / cB)));
-                int kaA[3], kaB[3];
+                ushort2 kaA[3], kaB[3];   // dump addresses of X[k], X[-k] for this lane's sampled frequencies
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const bool in = lane + 32 * i < kNS;
-                    kaA[i] = in ? (int)__ldg(p.kidx + (size_t)lamA * kNS + lane + 32 * i) : 0;
-                    kaB[i] = in ? (int)__ldg(p.kidx + (size_t)lamB * kNS + lane + 32 * i) : 0;
+                    kaA[i] = in ? __ldg(p.kaddr + (size_t)lamA * kNS + lane + 32 * i) : make_ushort2(0, 0);
+                    kaB[i] = in ? __ldg(p.kaddr + (size_t)lamB * kNS + lane + 32 * i) : make_ushort2(0, 0);
                 }
                 Z2 vf[40];
 #pragma unroll
@@ -332,8 +332,8 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        const float a = xf[nat_addr(kaA[i] % kNB)].x, am = xf[nat_addr(((kN - kaA[i]) % kN) % kNB)].x;
-                        const float b = xf[nat_addr(kaB[i] % kNB)].y, bm = xf[nat_addr(((kN - kaB[i]) % kN) % kNB)].y;
+                        const float a = xf[kaA[i].x].x, am = xf[kaA[i].y].x;
+                        const float b = xf[kaB[i].x].y, bm = xf[kaB[i].y].y;
                         if (cpt == 0) {
                             fa[i].x = a; fb[i].x = am; ga[i].x = b; gb[i].x = bm;
                         } else {
@@ -358,11 +358,11 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
                 double2* out = out_of(lam);
                 const double negc = -cl;
-                // sampled frequencies kA and their mirrors kB = -kA (indices into the length-N spectrum)
-                const uint16_t* kx = p.kidx + (size_t)lam * kNS;
-                int ka[3];
+                // where the sampled frequencies kA and their mirrors kB = -kA sit in the natural-order dump
+                const ushort2* kx = p.kaddr + (size_t)lam * kNS;
+                ushort2 ka[3];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
+                for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? __ldg(kx + lane + 32 * i) : make_ushort2(0, 0);
                 double2 za[3], zb[3];   // X[kA], X[kB] accumulated over the NF interleaved sub-sequences
                 // Cut and grade thresholds on D itself, tested on the integer pipe: a non-negative
                 // float (double) orders like its bit pattern (high word); the SIGNED compare keeps a
@@ -450,8 +450,8 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
-                            comp_set(fa[i], cpt, xb[nat_addr(ka[i] % kNB)]);
-                            comp_set(fb[i], cpt, xb[nat_addr(((kN - ka[i]) % kN) % kNB)]);
+                            comp_set(fa[i], cpt, xb[ka[i].x]);
+                            comp_set(fb[i], cpt, xb[ka[i].y]);
                         }
                         __syncwarp();
                     }
@@ -652,7 +652,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     using C = HotCfg<NF>;
     if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_kidx, c->d_wsamp, c->d_dmin, c->d_dphi32,
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_kaddr, c->d_wsamp, c->d_dmin, c->d_dphi32,
                 c->d_otf32, c->d_tw32, c->d_csort, c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;

@@ -80,6 +80,7 @@ struct Ctx {
     double* d_misc = nullptr;    // small: dirs, poslgs, lambda tables ...
     double* d_lam = nullptr;     // [max_lambda] c_lambda = 0.5 (2 pi/lambda_nm)^2
     uint16_t* d_kidx = nullptr;  // [max_lambda][kNS] sampled output indices (shifted by N/2)
+    ushort2* d_kaddr = nullptr;  // [max_lambda][kNS] dump addresses nat_addr(k mod 1280), nat_addr(-k mod 1280) of those
     double* d_frac = nullptr;    // [max_lambda][kPSF] bilinear fractions
     double* d_kern_tt = nullptr; // [max_planes][41][41] normalised tip-tilt kernels
     double* d_kern_mu = nullptr; // [max_lambda][41][41] normalised MUSE kernels
