@@ -161,6 +161,8 @@ def run_gpu(args):
         ctx.set_option(_lib.OPT_F32_ROWS, args.f32_rows)
     if args.exp_cut is not None:
         ctx.set_option(_lib.OPT_EXP_CUT, args.exp_cut)
+    if args.row_kernel is not None:
+        ctx.set_option(_lib.OPT_ROW_KERNEL, args.row_kernel)
 
     # ---- device-resident arm: inputs (draw records, tables) and outputs live in HBM
     recs = psfrec.draw_records(seeing, GL, L0, h)
@@ -299,6 +301,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--grade', type=float, default=None, help='PSFR_OPT_EXP_GRADE override (tuning)')
     ap.add_argument('--f32-rows', type=float, default=None, dest='f32_rows', help='PSFR_OPT_F32_ROWS override (tuning)')
+    ap.add_argument('--row-kernel', type=int, default=None, dest='row_kernel', help='PSFR_OPT_ROW_KERNEL override (tuning)')
     ap.add_argument('--exp-cut', type=float, default=None, dest='exp_cut', help='PSFR_OPT_EXP_CUT override (tuning)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -174,7 +174,10 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  * wavelengths): largest difference 8e-15 of the PSF peak, 8e-12 pointwise on pixels above
  * 1e-6 of the peak - the all-FP64 kernel and numpy differ by 1e-10 there.  A threshold >= the
  * cut disables the respective grade (e.g. 1e30). */
-enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3 };
+enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3,
+       /* 1 (default): one warp per row transform; 2: EXPERIMENTAL, one 160-thread group per
+        * transform held in shared memory (dim 1280, FP64 class only - csrc/psfr_hot2.cu) */
+       PSFR_OPT_ROW_KERNEL = 4 };
 PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
 
 /* Introspection used by tests and the bench --------------------------------------- */

@@ -25,6 +25,7 @@ E_CUDA, E_ARG, E_UNSUPPORTED, E_CAPACITY, E_STATE = -1, -2, -3, -4, -5
 OPT_EXP_CUT = 1
 OPT_EXP_GRADE = 2
 OPT_F32_ROWS = 3
+OPT_ROW_KERNEL = 4
 
 
 class PsfrError(RuntimeError):

@@ -644,6 +644,11 @@ int psfr_set_option(psfr_ctx* c, int key, double value) {
             if (!(value > 0)) return set_error(c, PSFR_E_ARG, "exp grade must be positive (got %g)", value);
             c->exp_grade = value;
             return PSFR_OK;
+        case PSFR_OPT_ROW_KERNEL:
+            if (value != 1.0 && value != 2.0) return set_error(c, PSFR_E_ARG, "row kernel must be 1 or 2 (got %g)", value);
+            if (value == 2.0 && c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "row kernel 2 is dim-1280 only");
+            c->row_kernel = (int)value;
+            return PSFR_OK;
         case PSFR_OPT_F32_ROWS:
             if (!(value > 0)) return set_error(c, PSFR_E_ARG, "f32 row threshold must be positive (got %g)", value);
             c->f32_rows = value;

@@ -656,14 +656,18 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
                 c->d_otf32, c->d_tw32, c->d_csort, c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
-    PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
-    int rc = hot_event(c, 0, s);
-    if (rc) return rc;
-    hot_rows_kernel<NF><<<grid, C::Warps * 32, C::Smem, s>>>(p, c->d_tw);
-    PSFR_LAUNCH_CHECK(c);
-    if ((rc = hot_event(c, 1, s))) return rc;
-    c->hot_launches += 1;
-    c->hot_psfs += (long long)nplanes * nlam;
+    int rc;
+    if (NF == 1 && c->row_kernel == 2) {
+        if ((rc = run_group_rows(c, nplanes, nlam, s))) return rc;
+    } else {
+        PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
+        if ((rc = hot_event(c, 0, s))) return rc;
+        hot_rows_kernel<NF><<<grid, C::Warps * 32, C::Smem, s>>>(p, c->d_tw);
+        PSFR_LAUNCH_CHECK(c);
+        if ((rc = hot_event(c, 1, s))) return rc;
+        c->hot_launches += 1;
+        c->hot_psfs += (long long)nplanes * nlam;
+    }
     // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
     // inverse transform); psf_muse averages the directions.
     if ((rc = ensure_dynamic_smem(c, hot_cols_kernel<NF>, ColCfg<NF>::Smem))) return rc;

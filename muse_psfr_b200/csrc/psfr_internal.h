@@ -72,6 +72,7 @@ struct Ctx {
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
     double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
     double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
+    int row_kernel = 1;          // 1: hot_rows_kernel; 2: the experimental group kernel of psfr_hot2.cu (PSFR_OPT_ROW_KERNEL)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples
@@ -170,6 +171,8 @@ int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_
 // row pass with fused exp(-c D) * OTF for nplanes x nlam, then pruned column pass summing
 // the ndir planes of each draw into d_samp [ndraw*nlam][80][80]
 int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s);
+// psfr_hot2.cu: experimental row pass (one transform per 160-thread group, data in shared memory)
+int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s);
 
 // ---- psfr_psd.cu ---------------------------------------------------------------------
 // uses d_draws, d_misc.  full: write the N x N PSD of every plane into d_psd (simul_psd_wfm);

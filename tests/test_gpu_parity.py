@@ -303,6 +303,23 @@ def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
         assert_image_close(full[k], ref[k])
 
 
+def test_experimental_group_row_kernel(psfrec, psd1):
+    """PSFR_OPT_ROW_KERNEL = 2 (csrc/psfr_hot2.cu: one 160-thread group per row transform, data in
+    shared memory) must give the planes of the production row kernel."""
+    from muse_psfr_b200 import _lib
+    ctx = psfrec.get_context()
+    bad = orc.simul_psd_wfm([0.36, 0.64], (100, 10000), 1.68, 19.9)
+    for psd, lam in ((psd1[0], np.array([500., 700., 900.])), (psd1[0], LBDA35), (bad[0], LBDA35[::4])):
+        ref = psfrec.psf_muse(psd, lam)
+        try:
+            ctx.set_option(_lib.OPT_ROW_KERNEL, 2)
+            got = psfrec.psf_muse(psd, lam)
+        finally:
+            ctx.set_option(_lib.OPT_ROW_KERNEL, 1)
+        assert np.isfinite(got).all()
+        assert rel_to_peak(got, ref) < 1e-13
+
+
 def test_wavelength_below_grid_limit(psfrec, psd1):
     with pytest.raises(ValueError):
         psfrec.psf_muse(psd1[0], np.array([400.]))      # needs a 1552-pixel crop: reference fails too
@@ -490,6 +507,7 @@ def test_c_abi_argument_errors(psfrec):
     assert lib.psfr_set_option(ctx._h, _lib.OPT_EXP_CUT, -1.0) == _lib.E_ARG
     assert lib.psfr_set_option(ctx._h, _lib.OPT_EXP_GRADE, 0.0) == _lib.E_ARG
     assert lib.psfr_set_option(ctx._h, _lib.OPT_F32_ROWS, -3.0) == _lib.E_ARG
+    assert lib.psfr_set_option(ctx._h, _lib.OPT_ROW_KERNEL, 3.0) == _lib.E_ARG
     assert lib.psfr_psf_cube(ctx._h, 1, 1, ctx.max_lambda + 1, _lib.ptr(np.full(ctx.max_lambda + 1, 600.)),
                              _lib.ptr(out), None) < 0
     with pytest.raises(_lib.PsfrError):
