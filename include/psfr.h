@@ -175,8 +175,9 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  * 1e-6 of the peak - the all-FP64 kernel and numpy differ by 1e-10 there.  A threshold >= the
  * cut disables the respective grade (e.g. 1e30). */
 enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3,
-       /* 1 (default): one warp per row transform; 2: EXPERIMENTAL, one 160-thread group per
-        * transform held in shared memory (dim 1280, FP64 class only - csrc/psfr_hot2.cu) */
+       /* row kernel of the pruned stage B at dim 1280: 2 (default) one 160-thread group per row
+        * transform, data in shared memory (csrc/psfr_hot2.cu); 1 one warp per transform, data in
+        * registers (csrc/psfr_hot.cu, the only one at dim 2560) */
        PSFR_OPT_ROW_KERNEL = 4 };
 PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
 

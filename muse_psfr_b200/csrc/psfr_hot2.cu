@@ -1,6 +1,6 @@
-// EXPERIMENTAL alternative to hot_rows_kernel (psfr_hot.cu), dim 1280 only, selected with
-// PSFR_OPT_ROW_KERNEL = 2.  Same work, same stream of units, same ring; what differs is who
-// runs a transform:
+// Row kernel of the pruned stage B at dim 1280 (PSFR_OPT_ROW_KERNEL = 2, the default; 1 selects
+// hot_rows_kernel of psfr_hot.cu, which also serves dim 2560).  Same work, same stream of units,
+// same ring; what differs is who runs a transform:
 //
 //   hot_rows_kernel : one WARP = one 1280-point transform, 40 points per lane in registers,
 //                     ~70 KB of unrolled code per unit, 8 warps per SM (253 registers);
@@ -18,8 +18,8 @@
 // The strides 172 / 21 and the skews make every 16-byte access pattern above conflict-free
 // (quarter-warps hit eight distinct 16-byte slots).
 //
-// Only the FP64 class is implemented (units that hot_rows_kernel runs in single precision take
-// the FP64 transform with the single-precision exp), so compare it with --f32-rows 1e30.
+// Row pairs below exp(-f32_min) run the same passes on float2 data in the same buffer (one
+// wavelength per transform: no packed pairs here).
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 #include "tma.cuh"
@@ -52,13 +52,98 @@ struct Rows2Params {
     const double* dmin;    // [nplanes][kRows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
+    const float2* tw32;    // single-precision twiddles (global memory, L1-resident)
     int* next_item;
-    double cut, grade;
+    double cut, grade, f32_min;
     int nplanes, nlam;
 };
 
 __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGT) : "memory");
+}
+
+// element strides of the pass-1/2 layout buf[k1 * S + m * 21 + n3]: 172 for 16-byte elements, 168 for
+// 8-byte ones (quarter- / half-warps then hit distinct 16- / 8-byte slots in the radix-20 loads)
+template <class Z>
+struct RowStride {
+    static constexpr int S = sizeof(Z) == 16 ? 172 : 168;
+};
+
+// twiddles of a thread's two radix-8 butterflies: w_N^(b k1) and w_160^(n3 k2), k = 1..7: the FP64
+// ones from the shared-memory tables, the FP32 ones from the L1-resident float table
+struct TwSmem {
+    const double2* p1;  // + (j*7)*32 + t, shared memory
+    const double2* p2;  // + n3
+    __device__ __forceinline__ double2 tw1(int k1) const { return p1[(k1 - 1) * 32]; }
+    __device__ __forceinline__ double2 tw2(int k2) const { return p2[(k2 - 1) * kR3]; }
+};
+struct TwMem32 {
+    const float2* p1;   // + (j*7)*32 + t
+    const float2* p2;   // + n3
+    __device__ __forceinline__ float2 tw1(int k1) const { return __ldg(p1 + (k1 - 1) * 32); }
+    __device__ __forceinline__ float2 tw2(int k2) const { return __ldg(p2 + (k2 - 1) * kR3); }
+};
+
+// passes of one transform on the group's buffer, from the eight pass-1 inputs of every thread to the
+// store of the 80 sampled frequencies of both rows (see the file header for the index maps).
+template <class Z, class TW>
+__device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
+                                                const uint16_t* __restrict__ kidx, double2* __restrict__ out) {
+    constexpr int S = RowStride<Z>::S;
+    const int n2 = b / 20, n3 = b % 20;
+    dft8(x);
+    buf[n2 * 21 + n3] = x[0];
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S + n2 * 21 + n3] = cmul(x[k1], tw.tw1(k1));
+    group_bar(grp);
+    // ---- pass 2: radix-8 over n2 (thread = (k1, n3) with k1 = b / 20), twiddle, in place
+    {
+        Z* col = buf + n2 * S + n3;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) x[m] = col[m * 21];
+        dft8(x);
+        col[0] = x[0];
+#pragma unroll
+        for (int k2 = 1; k2 < 8; ++k2) col[k2 * 21] = cmul(x[k2], tw.tw2(k2));
+    }
+    group_bar(grp);
+    // ---- pass 3: radix-20 over n3 by the first two warps of the group (rows k2-fastest: a quarter-
+    // warp hits eight distinct 16-byte slots), natural-order output.  Splitting it into 4 x 5
+    // sub-passes over all 160 threads was measured SLOWER (3.63 vs 3.38 ms per chunk: one more
+    // barrier and one more trip through shared memory cost more than the idle warps).
+    if (b < 64) {
+        const int k2 = b & 7, k1 = b >> 3;
+        Z z[20];
+        const Z* row = buf + k1 * S + k2 * 21;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) z[i] = row[i];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + kGroups + grp) : "memory");   // all rows read before any is overwritten
+        dft_r3<kR3>(z);
+        const int k0 = k1 + 8 * k2;
+#pragma unroll
+        for (int k3 = 0; k3 < 20; ++k3) {
+            const int k = k0 + 64 * k3;
+            buf[k + (k >> 3)] = z[k3];
+        }
+    }
+    group_bar(grp);
+    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y]
+    {
+        const int y = b >> 1;
+        const int k = (int)__ldg(kidx + y);
+        const int kk = (b & 1) ? (kN - k) % kN : k;
+        const Z m = buf[kk + (kk >> 3)];
+        const double2 mine = make_double2((double)m.x, (double)m.y);
+        double2 other;
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+        other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+        if (!(b & 1)) {
+            const double2 za = mine, zb = other;
+            st_global_256(out + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                          make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+        }
+    }
+    group_bar(grp);   // the buffer is free for the next unit
 }
 
 __global__ void __launch_bounds__(kGroups* kGT, 1)
@@ -67,7 +152,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);
     volatile int* item_of = released + kStages;
-    volatile int* la_of = item_of + kStages;
+    volatile int* la_of = item_of + kStages;   // sorted positions [0, la) dead, [la, lb) single precision,
+    volatile int* lb_of = la_of + kStages;     //   [lb, nlam) FP64 (as in hot_rows_kernel)
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
     double* ring = reinterpret_cast<double*>(tw2 + G::TW2);
@@ -95,7 +181,14 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 if (c_of(mid) * dm > p.cut) lo = mid + 1; else hi = mid;
             }
             la_of[s] = lo;
-            if (lo == p.nlam) {
+            const int la = lo;
+            hi = p.nlam;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (c_of(mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
+            }
+            lb_of[s] = lo;
+            if (la == p.nlam) {
                 mbar_arrive(full + s);
                 return;
             }
@@ -113,6 +206,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     };
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
+    const TwSmem twr{tw1 + ((b >> 5) * 7) * 32 + (b & 31), tw2 + b % 20};
+    const TwMem32 twm{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + b % 20};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
@@ -175,7 +270,6 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         }
     };
 
-    const int n2 = b / 20, n3 = b % 20;     // pass-1 role; pass 2: k1 = n2, same n3
 #pragma unroll 1
     for (;;) {
         int rel = base + grp;
@@ -195,78 +289,42 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         const int cut32 = __float_as_int((float)(p.cut * rcl));
         const int grade32 = __float_as_int((float)(p.grade * rcl));
 
-        // ---- pass 1: inputs, radix-8 over n1, twiddle
-        double2 x[8];
+        const uint16_t* kx = p.kidx + (size_t)lam * kNS;
+        double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
+        if (pos < lb_of[s]) {
+            // ---- single-precision unit (every entry below exp(-f32_min) of the OTF peak): inputs,
+            // transform and buffer in FP32
+            float2 x[8];
 #pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) {
-            const int n = n1 * 160 + b;
-            const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
-            const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
-            const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
-            const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
-            const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
-            if (__all_sync(0xffffffffu, dead)) {
-                x[n1] = make_double2(0.0, 0.0);
-            } else if (__all_sync(0xffffffffu, cheap)) {
-                x[n1] = make_double2(f2d_bits(ex2_approx(negc2f * d0) * t0), f2d_bits(ex2_approx(negc2f * d1) * t1));
-            } else {
-                x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const int n = n1 * 160 + b;
+                const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
+                const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
+                if (__all_sync(0xffffffffu, dead)) x[n1] = make_float2(0.f, 0.f);
+                else x[n1] = make_float2(ex2_approx(negc2f * d0) * t0, ex2_approx(negc2f * d1) * t1);
             }
-        }
-        dft8(x);
-        {
-            const int j = b >> 5, t = b & 31;
-            buf[n2 * 21 + n3] = x[0];
+            group_transform(x, reinterpret_cast<float2*>(buf), twm, b, grp, kx, out);
+        } else {
+            // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
+            double2 x[8];
 #pragma unroll
-            for (int k1 = 1; k1 < 8; ++k1)
-                buf[k1 * 172 + n2 * 21 + n3] = cmul(x[k1], tw1[(j * 7 + (k1 - 1)) * 32 + t]);
-        }
-        group_bar(grp);
-        // ---- pass 2: radix-8 over n2 (thread = (k1, n3) with k1 = b / 20), twiddle, in place
-        {
-            double2* col = buf + n2 * 172 + n3;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) x[m] = col[m * 21];
-            dft8(x);
-            col[0] = x[0];
-#pragma unroll
-            for (int k2 = 1; k2 < 8; ++k2) col[k2 * 21] = cmul(x[k2], tw2[(k2 - 1) * kR3 + n3]);
-        }
-        group_bar(grp);
-        // ---- pass 3: radix-20 over n3 by the first two warps of the group, natural-order output
-        if (b < 64) {
-            const int k2 = b & 7, k1 = b >> 3;
-            double2 z[20];
-            const double2* row = buf + k1 * 172 + k2 * 21;
-#pragma unroll
-            for (int i = 0; i < 20; ++i) z[i] = row[i];
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + kGroups + grp) : "memory");   // all rows read before any is overwritten
-            dft_r3<kR3>(z);
-            const int k0 = k1 + 8 * k2;
-#pragma unroll
-            for (int k3 = 0; k3 < 20; ++k3) {
-                const int k = k0 + 64 * k3;
-                buf[k + (k >> 3)] = z[k3];
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const int n = n1 * 160 + b;
+                const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
+                const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
+                const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
+                const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
+                const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
+                if (__all_sync(0xffffffffu, dead)) {
+                    x[n1] = make_double2(0.0, 0.0);
+                } else if (__all_sync(0xffffffffu, cheap)) {
+                    x[n1] = make_double2(f2d_bits(ex2_approx(negc2f * d0) * t0), f2d_bits(ex2_approx(negc2f * d1) * t1));
+                } else {
+                    x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+                }
             }
+            group_transform(x, buf, twr, b, grp, kx, out);
         }
-        group_bar(grp);
-        // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y]
-        {
-            const int y = b >> 1;
-            const int k = (int)__ldg(p.kidx + (size_t)lam * kNS + y);
-            const int kk = (b & 1) ? (kN - k) % kN : k;
-            const double2 mine = buf[kk + (kk >> 3)];
-            double2 other;
-            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-            other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-            if (!(b & 1)) {
-                const double2 za = mine, zb = other;
-                st_global_256(p.Y + (((size_t)plane * p.nlam + lam) * kNS + y) * kRows + 2 * rp,
-                              make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
-                              make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
-            }
-        }
-        group_bar(grp);   // the buffer is free for the next unit
         base += kGroups;
     }
 }
@@ -277,7 +335,7 @@ int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
     if (c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "the group row kernel is dim-1280 only");
     if (int rc = ensure_dynamic_smem(c, group_rows_kernel, kSmem2)) return rc;
     Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_kidx, c->d_dmin, c->d_csort,
-                  c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, nplanes, nlam};
+                  c->d_lorder, c->d_tw32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * kPairs) grid = nplanes * kPairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));

@@ -72,7 +72,7 @@ struct Ctx {
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
     double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
     double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
-    int row_kernel = 1;          // 1: hot_rows_kernel; 2: the experimental group kernel of psfr_hot2.cu (PSFR_OPT_ROW_KERNEL)
+    int row_kernel = 2;          // dim 1280: 2 group_rows_kernel (psfr_hot2.cu), 1 hot_rows_kernel (PSFR_OPT_ROW_KERNEL)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples

@@ -303,22 +303,26 @@ def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
         assert_image_close(full[k], ref[k])
 
 
-def test_experimental_group_row_kernel(psfrec, psd1):
-    """PSFR_OPT_ROW_KERNEL = 2 (csrc/psfr_hot2.cu: one 160-thread group per row transform, data in
-    shared memory) must give the planes of the production row kernel."""
+def test_row_kernels_agree(psfrec, psd1):
+    """The two row kernels of dim 1280 - PSFR_OPT_ROW_KERNEL = 2 (default, csrc/psfr_hot2.cu: one
+    160-thread group per row transform, data in shared memory) and 1 (csrc/psfr_hot.cu: one warp per
+    transform, data in registers) - must give the same planes."""
     from muse_psfr_b200 import _lib
     ctx = psfrec.get_context()
     bad = orc.simul_psd_wfm([0.36, 0.64], (100, 10000), 1.68, 19.9)
     for psd, lam in ((psd1[0], np.array([500., 700., 900.])), (psd1[0], LBDA35), (bad[0], LBDA35[::4])):
         ref = psfrec.psf_muse(psd, lam)
         try:
-            ctx.set_option(_lib.OPT_ROW_KERNEL, 2)
+            ctx.set_option(_lib.OPT_ROW_KERNEL, 1)
             got = psfrec.psf_muse(psd, lam)
         finally:
-            ctx.set_option(_lib.OPT_ROW_KERNEL, 1)
+            ctx.set_option(_lib.OPT_ROW_KERNEL, 2)
         assert np.isfinite(got).all()
         assert rel_to_peak(got, ref) < 1e-13
-
+        want = orc.psf_muse(psd, lam[:2])
+        for k in range(2):
+            assert_image_close(got[k], want[k])
+            assert_image_close(ref[k], want[k])
 
 def test_wavelength_below_grid_limit(psfrec, psd1):
     with pytest.raises(ValueError):
