@@ -16,7 +16,8 @@
 //   pass 3 : threads (k1, k2) < 64: radix-20 over n3 -> natural order buf[k + (k >> 3)]
 //   gather : thread pairs (2y, 2y+1) read X[k_y], X[-k_y], untangle the two real rows, store.
 // The strides 172 / 21 and the skews make every 16-byte access pattern above conflict-free
-// (quarter-warps hit eight distinct 16-byte slots).
+// (quarter-warps hit eight distinct 16-byte slots); single-precision units use their own
+// stride and thread roles (struct Lay).
 //
 // Row pairs below exp(-f32_min) run the same passes on float2 data in the same buffer (one
 // wavelength per transform: no packed pairs here).
@@ -62,11 +63,28 @@ __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGT) : "memory");
 }
 
-// element strides of the pass-1/2 layout buf[k1 * S + m * 21 + n3]: 172 for 16-byte elements, 168 for
-// 8-byte ones (quarter- / half-warps then hit distinct 16- / 8-byte slots in the radix-20 loads)
+// Layout buf[k1 * S + m * 21 + n3] of passes 1/2 and who does what in passes 2 and 3, per element
+// size.  16-byte elements (a quarter-warp must hit 8 distinct 16-byte slots): S = 172, pass 2 with
+// n3 fastest along the lanes, pass 3 with k2 fastest.  8-byte elements (a half-warp must hit 16
+// distinct 8-byte slots): S = 178 (= 2 mod 16) and k1 fastest in both passes, so that a half-warp
+// sees 2 k1 + {n3, n3 + 1} resp. 2 k1 + 5 {k2, k2 + 1}.
 template <class Z>
-struct RowStride {
-    static constexpr int S = sizeof(Z) == 16 ? 172 : 168;
+struct Lay;
+template <>
+struct Lay<double2> {
+    static constexpr int S = 172;
+    __device__ static int p2_k1(int b) { return b / 20; }
+    __device__ static int p2_n3(int b) { return b % 20; }
+    __device__ static int p3_k1(int b) { return b >> 3; }
+    __device__ static int p3_k2(int b) { return b & 7; }
+};
+template <>
+struct Lay<float2> {
+    static constexpr int S = 178;
+    __device__ static int p2_k1(int b) { return b & 7; }
+    __device__ static int p2_n3(int b) { return b >> 3; }
+    __device__ static int p3_k1(int b) { return b & 7; }
+    __device__ static int p3_k2(int b) { return b >> 3; }
 };
 
 // twiddles of a thread's two radix-8 butterflies: w_N^(b k1) and w_160^(n3 k2), k = 1..7: the FP64
@@ -89,16 +107,17 @@ struct TwMem32 {
 template <class Z, class TW>
 __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
                                                 const uint16_t* __restrict__ kidx, double2* __restrict__ out) {
-    constexpr int S = RowStride<Z>::S;
+    using L = Lay<Z>;
+    constexpr int S = L::S;
     const int n2 = b / 20, n3 = b % 20;
     dft8(x);
     buf[n2 * 21 + n3] = x[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S + n2 * 21 + n3] = cmul(x[k1], tw.tw1(k1));
     group_bar(grp);
-    // ---- pass 2: radix-8 over n2 (thread = (k1, n3) with k1 = b / 20), twiddle, in place
+    // ---- pass 2: radix-8 over n2 (thread = (k1, n3), see Lay), twiddle, in place
     {
-        Z* col = buf + n2 * S + n3;
+        Z* col = buf + L::p2_k1(b) * S + L::p2_n3(b);
 #pragma unroll
         for (int m = 0; m < 8; ++m) x[m] = col[m * 21];
         dft8(x);
@@ -112,7 +131,7 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
     // sub-passes over all 160 threads was measured SLOWER (3.63 vs 3.38 ms per chunk: one more
     // barrier and one more trip through shared memory cost more than the idle warps).
     if (b < 64) {
-        const int k2 = b & 7, k1 = b >> 3;
+        const int k2 = L::p3_k2(b), k1 = L::p3_k1(b);
         Z z[20];
         const Z* row = buf + k1 * S + k2 * 21;
 #pragma unroll
@@ -206,8 +225,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     };
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
-    const TwSmem twr{tw1 + ((b >> 5) * 7) * 32 + (b & 31), tw2 + b % 20};
-    const TwMem32 twm{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + b % 20};
+    const TwSmem twr{tw1 + ((b >> 5) * 7) * 32 + (b & 31), tw2 + Lay<double2>::p2_n3(b)};
+    const TwMem32 twm{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + Lay<float2>::p2_n3(b)};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
