@@ -111,6 +111,7 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
     constexpr int S = L::S;
     const int n2 = b / 20, n3 = b % 20;
     dft8(x);
+    group_bar(grp);   // the gather of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
     buf[n2 * 21 + n3] = x[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S + n2 * 21 + n3] = cmul(x[k1], tw.tw1(k1));
@@ -162,7 +163,6 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
                           make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
         }
     }
-    group_bar(grp);   // the buffer is free for the next unit
 }
 
 __global__ void __launch_bounds__(kGroups* kGT, 1)
