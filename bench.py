@@ -273,7 +273,7 @@ def run_gpu(args):
                 'h2d_bytes_per_step': int(recs.nbytes + dirs.nbytes + pos.nbytes + LBDA.nbytes),
                 'd2h_bytes_per_step': int(h_cube.numel() * 8 + h_fit.numel() * 8)},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'hot_rows_kernel (stage-B row pass: exp(-c D)*OTF + 1280-pt FFT, pruned)',
+        'roofline': {'bound': 'hbm', 'kernel': 'stage-B row kernel (group_rows_kernel, or hot_rows_kernel with --row-kernel 1: exp(-c D)*OTF + 1280-pt FFT, pruned)',
                      'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
                      'algorithmic_bytes_per_psf': BYTES_STAGE_B, 'psfs_per_launch': hot_psfs / max(hot_n, 1),
