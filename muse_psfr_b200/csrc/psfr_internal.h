@@ -171,7 +171,7 @@ int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_
 // row pass with fused exp(-c D) * OTF for nplanes x nlam, then pruned column pass summing
 // the ndir planes of each draw into d_samp [ndraw*nlam][80][80]
 int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s);
-// psfr_hot2.cu: experimental row pass (one transform per 160-thread group, data in shared memory)
+// psfr_hot2.cu: the dim-1280 row pass (one transform per 160-thread group, data in shared memory)
 int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s);
 
 // ---- psfr_psd.cu ---------------------------------------------------------------------
