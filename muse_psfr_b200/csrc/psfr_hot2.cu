@@ -40,7 +40,7 @@ constexpr uint32_t kStageBytes = 2 * kTileBytes + 2 * kTileBytes32;
 constexpr size_t kStageDoubles = kStageBytes / sizeof(double);
 constexpr int kStages = 2, kTabMax = 64;
 constexpr size_t kSmem2 = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) + (size_t)kStages * kStageBytes +
-                          (size_t)kGroups * kBuf * sizeof(double2) + kTabMax * (2 * sizeof(double) + sizeof(int));
+                          (size_t)kGroups * kBuf * sizeof(double2) + kTabMax * (2 * sizeof(double) + 4 * sizeof(int));
 static_assert(kSmem2 <= 232448, "group kernel shared memory exceeds the 227 KB per-CTA limit");
 
 struct Rows2Params {
@@ -180,6 +180,9 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     double* tab_c = reinterpret_cast<double*>(bufs + (size_t)kGroups * kBuf);
     double* tab_rc = tab_c + kTabMax;
     int* tab_lo = reinterpret_cast<int*>(tab_rc + kTabMax);
+    int* tab_cut = tab_lo + kTabMax;      // per sorted wavelength: float bit patterns of cut / c, grade / c
+    int* tab_grade = tab_cut + kTabMax;   //   and of -c log2(e) (the single-precision exp is 2^(that * D))
+    int* tab_n2f = tab_grade + kTabMax;
     const int grp = threadIdx.x / kGT, b = threadIdx.x % kGT, lane = threadIdx.x & 31;
     double2* buf = bufs + (size_t)grp * kBuf;
     const int items = p.nplanes * kPairs;
@@ -233,6 +236,9 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
             tab_c[i] = cv;
             tab_rc[i] = 1.0 / cv;
             tab_lo[i] = __ldg(p.lorder + i);
+            tab_cut[i] = __float_as_int((float)(p.cut * (1.0 / cv)));
+            tab_grade[i] = __float_as_int((float)(p.grade * (1.0 / cv)));
+            tab_n2f[i] = __float_as_int((float)(-cv * 1.44269504088896338700));
         }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -304,9 +310,9 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         const float* sT32 = sD32 + kTile;
         const int plane = item / kPairs, rp = item % kPairs;
         const double negc = -cl;
-        const float negc2f = (float)(negc * 1.44269504088896338700);
-        const int cut32 = __float_as_int((float)(p.cut * rcl));
-        const int grade32 = __float_as_int((float)(p.grade * rcl));
+        const float negc2f = tabbed ? __int_as_float(tab_n2f[pos]) : (float)(negc * 1.44269504088896338700);
+        const int cut32 = tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut * rcl));
+        const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
 
         const uint16_t* kx = p.kidx + (size_t)lam * kNS;
         double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
