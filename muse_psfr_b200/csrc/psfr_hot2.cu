@@ -130,7 +130,9 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
     // ---- pass 3: radix-20 over n3 by the first two warps of the group (rows k2-fastest: a quarter-
     // warp hits eight distinct 16-byte slots), natural-order output.  Splitting it into 4 x 5
     // sub-passes over all 160 threads was measured SLOWER (3.63 vs 3.38 ms per chunk: one more
-    // barrier and one more trip through shared memory cost more than the idle warps).
+    // barrier and one more trip through shared memory cost more than the idle warps), and so was
+    // giving a row to two threads (even / odd outputs, each a 10-point transform of the folded
+    // row: 3.36 vs 3.21 ms - every row is then read twice, and the kernel is shared-memory-bound).
     if (b < 64) {
         const int k2 = L::p3_k2(b), k1 = L::p3_k1(b);
         Z z[20];
