@@ -217,6 +217,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     c->max_planes = max_planes;
     c->max_lambda = max_lambda;
     c->NF = dim / kNB;
+    c->row_kernel = c->NF == 1 ? 2 : 1;   // the group row kernel exists for dim 1280 only
     c->N = dim;
     c->NH = dim / 2;
     c->rows = dim / 2 + 2;

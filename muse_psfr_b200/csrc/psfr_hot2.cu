@@ -185,7 +185,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     int* tab_cut = tab_lo + kTabMax;      // per sorted wavelength: float bit patterns of cut / c, grade / c
     int* tab_grade = tab_cut + kTabMax;   //   and of -c log2(e) (the single-precision exp is 2^(that * D))
     int* tab_n2f = tab_grade + kTabMax;
-    const int grp = threadIdx.x / kGT, b = threadIdx.x % kGT, lane = threadIdx.x & 31;
+    const int grp = threadIdx.x / kGT, b = threadIdx.x % kGT;
     double2* buf = bufs + (size_t)grp * kBuf;
     const int items = p.nplanes * kPairs;
     const bool tabbed = p.nlam <= kTabMax;
