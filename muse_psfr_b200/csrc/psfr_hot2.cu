@@ -16,11 +16,10 @@
 //   pass 3 : threads (k1, k2) < 64: radix-20 over n3 -> natural order buf[k + (k >> 3)]
 //   gather : thread pairs (2y, 2y+1) read X[k_y], X[-k_y], untangle the two real rows, store.
 // The strides 172 / 21 and the skews make every 16-byte access pattern above conflict-free
-// (quarter-warps hit eight distinct 16-byte slots); single-precision units use their own
-// stride and thread roles (struct Lay).
+// (quarter-warps hit eight distinct 16-byte slots).
 //
-// Row pairs below exp(-f32_min) run the same passes on float2 data in the same buffer (one
-// wavelength per transform: no packed pairs here).
+// Row pairs below exp(-f32_min) run the same passes in single precision, two wavelengths at a time
+// as the halves of one packed transform (Z2, warp_fft.cuh).
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 #include "tma.cuh"
@@ -63,50 +62,48 @@ __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGT) : "memory");
 }
 
-// Layout buf[k1 * S + m * 21 + n3] of passes 1/2 and who does what in passes 2 and 3, per element
-// size.  16-byte elements (a quarter-warp must hit 8 distinct 16-byte slots): S = 172, pass 2 with
-// n3 fastest along the lanes, pass 3 with k2 fastest.  8-byte elements (a half-warp must hit 16
-// distinct 8-byte slots): S = 178 (= 2 mod 16) and k1 fastest in both passes, so that a half-warp
-// sees 2 k1 + {n3, n3 + 1} resp. 2 k1 + 5 {k2, k2 + 1}.
+// Layout buf[k1 * S + m * 21 + n3] of passes 1/2 and who does what in passes 2 and 3.  Both element
+// types are 16 bytes (a double2, or the packed pair Z2): a quarter-warp must hit 8 distinct
+// 16-byte slots, which S = 172, pass 2 with n3 fastest along the lanes and pass 3 with k2 fastest
+// achieve.
 template <class Z>
-struct Lay;
-template <>
-struct Lay<double2> {
+struct Lay {
+    static_assert(sizeof(Z) == 16, "the layouts are chosen for 16-byte elements");
     static constexpr int S = 172;
     __device__ static int p2_k1(int b) { return b / 20; }
     __device__ static int p2_n3(int b) { return b % 20; }
     __device__ static int p3_k1(int b) { return b >> 3; }
     __device__ static int p3_k2(int b) { return b & 7; }
 };
-template <>
-struct Lay<float2> {
-    static constexpr int S = 178;
-    __device__ static int p2_k1(int b) { return b & 7; }
-    __device__ static int p2_n3(int b) { return b >> 3; }
-    __device__ static int p3_k1(int b) { return b & 7; }
-    __device__ static int p3_k2(int b) { return b >> 3; }
-};
 
 // twiddles of a thread's two radix-8 butterflies: w_N^(b k1) and w_160^(n3 k2), k = 1..7: the FP64
-// ones from the shared-memory tables, the FP32 ones from the L1-resident float table
+// ones from the shared-memory tables, the single-precision ones from the L1-resident float table
 struct TwSmem {
     const double2* p1;  // + (j*7)*32 + t, shared memory
     const double2* p2;  // + n3
     __device__ __forceinline__ double2 tw1(int k1) const { return p1[(k1 - 1) * 32]; }
     __device__ __forceinline__ double2 tw2(int k2) const { return p2[(k2 - 1) * kR3]; }
 };
-struct TwMem32 {
-    const float2* p1;   // + (j*7)*32 + t
-    const float2* p2;   // + n3
-    __device__ __forceinline__ float2 tw1(int k1) const { return __ldg(p1 + (k1 - 1) * 32); }
-    __device__ __forceinline__ float2 tw2(int k2) const { return __ldg(p2 + (k2 - 1) * kR3); }
+struct TwMem32Pair {   // the same float table, broadcast into both halves of a packed pair
+    const float2* p1;
+    const float2* p2;
+    __device__ __forceinline__ Z2 tw1(int k1) const { return ztw<Z2>(__ldg(p1 + (k1 - 1) * 32)); }
+    __device__ __forceinline__ Z2 tw2(int k2) const { return ztw<Z2>(__ldg(p2 + (k2 - 1) * kR3)); }
 };
+
+// one half (wavelength) of a packed pair / the value itself, as FP64
+__device__ __forceinline__ double2 half_of(const Z2& m, int h) {
+    return h ? make_double2((double)m.x.v.y, (double)m.y.v.y) : make_double2((double)m.x.v.x, (double)m.y.v.x);
+}
+__device__ __forceinline__ double2 half_of(const double2& m, int) { return m; }
 
 // passes of one transform on the group's buffer, from the eight pass-1 inputs of every thread to the
 // store of the 80 sampled frequencies of both rows (see the file header for the index maps).
 template <class Z, class TW>
 __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
-                                                const uint16_t* __restrict__ kidx, double2* __restrict__ out) {
+                                                const uint16_t* __restrict__ kidx, double2* __restrict__ out,
+                                                const uint16_t* __restrict__ kidx2 = nullptr,
+                                                double2* __restrict__ out2 = nullptr) {
     using L = Lay<Z>;
     constexpr int S = L::S;
     const int n2 = b / 20, n3 = b % 20;
@@ -149,19 +146,23 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
         }
     }
     group_bar(grp);
-    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y]
-    {
+    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y]; a packed pair
+    // does it once per wavelength (each has its own sampled frequencies), reading its half
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint16_t* kx = h ? kidx2 : kidx;
+        double2* o = h ? out2 : out;
+        if (h && o == nullptr) break;   // a single transform, or a pair with only one wavelength
         const int y = b >> 1;
-        const int k = (int)__ldg(kidx + y);
+        const int k = (int)__ldg(kx + y);
         const int kk = (b & 1) ? (kN - k) % kN : k;
-        const Z m = buf[kk + (kk >> 3)];
-        const double2 mine = make_double2((double)m.x, (double)m.y);
+        const double2 mine = half_of(buf[kk + (kk >> 3)], h);
         double2 other;
         other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
         other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
         if (!(b & 1)) {
             const double2 za = mine, zb = other;
-            st_global_256(out + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+            st_global_256(o + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
                           make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
         }
     }
@@ -175,6 +176,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     volatile int* item_of = released + kStages;
     volatile int* la_of = item_of + kStages;   // sorted positions [0, la) dead, [la, lb) single precision,
     volatile int* lb_of = la_of + kStages;     //   [lb, nlam) FP64 (as in hot_rows_kernel)
+    volatile int* ns_of = lb_of + kStages;     // stream slots of the item: pairs of single-precision units, FP64 units
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
     double2* tw2 = tw1 + G::TW1;
     double* ring = reinterpret_cast<double*>(tw2 + G::TW2);
@@ -212,6 +214,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 if (c_of(mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
             }
             lb_of[s] = lo;
+            ns_of[s] = (lo - la + 1) / 2 + (p.nlam - lo);
             if (la == p.nlam) {
                 mbar_arrive(full + s);
                 return;
@@ -231,7 +234,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
 
     for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
     const TwSmem twr{tw1 + ((b >> 5) * 7) * 32 + (b & 31), tw2 + Lay<double2>::p2_n3(b)};
-    const TwMem32 twm{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + Lay<float2>::p2_n3(b)};
+    const TwMem32Pair twp{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + Lay<Z2>::p2_n3(b)};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
@@ -277,7 +280,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 }
             }
             if (item_of[s] < 0) return false;
-            const int n = p.nlam - la_of[s];
+            const int n = ns_of[s];
             if (rel < n) return true;
             rel -= n;
             base -= n;
@@ -303,36 +306,58 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         if (!seek(rel)) break;
         const int s = cur % kStages;
         const int item = item_of[s];
-        const int pos = (cur & 1) ? p.nlam - 1 - rel : la_of[s] + rel;
-        const int lam = tabbed ? tab_lo[pos] : __ldg(p.lorder + pos);
-        const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
+        // slot -> units (sorted positions): the first npair slots of an item hold two single-precision
+        // units each (the last one may hold one), the others one FP64 unit; odd items run backwards
+        const int la = la_of[s], lb = lb_of[s], npair = (lb - la + 1) / 2;
+        const int slot = (cur & 1) ? ns_of[s] - 1 - rel : rel;
         const double* sD = ring + (size_t)s * kStageDoubles;
         const double* sT = sD + kTile;
         const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);
         const float* sT32 = sD32 + kTile;
         const int plane = item / kPairs, rp = item % kPairs;
-        const double negc = -cl;
-        const float negc2f = tabbed ? __int_as_float(tab_n2f[pos]) : (float)(negc * 1.44269504088896338700);
-        const int cut32 = tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut * rcl));
-        const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
-
-        const uint16_t* kx = p.kidx + (size_t)lam * kNS;
-        double2* out = p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp;
-        if (pos < lb_of[s]) {
-            // ---- single-precision unit (every entry below exp(-f32_min) of the OTF peak): inputs,
-            // transform and buffer in FP32
-            float2 x[8];
+        auto lam_of = [&](int pos) { return tabbed ? tab_lo[pos] : __ldg(p.lorder + pos); };
+        auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp; };
+        auto n2f_of = [&](int pos) {
+            return tabbed ? __int_as_float(tab_n2f[pos]) : (float)(-c_of(pos) * 1.44269504088896338700);
+        };
+        auto cut_of = [&](int pos) {
+            return tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut / c_of(pos)));
+        };
+        if (slot < npair) {
+            // ---- single-precision pair (every entry below exp(-f32_min) of the OTF peak at both
+            // wavelengths): inputs, transform and buffer in FP32, the two wavelengths as the two halves
+            // of one packed transform (Z2: FADD2 / FMUL2 / FFMA2)
+            const int posA = la + 2 * slot;
+            const bool two = posA + 1 < lb;
+            const int posB = two ? posA + 1 : posA;
+            const int lamA = lam_of(posA), lamB = lam_of(posB);
+            const float nA = n2f_of(posA), nB = n2f_of(posB);
+            const int cut32 = cut_of(posB);   // c_B <= c_A: an entry below the cut at B is below it at A
+            Z2 x[8];
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
                 const int n = n1 * 160 + b;
                 const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
                 const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
-                if (__all_sync(0xffffffffu, dead)) x[n1] = make_float2(0.f, 0.f);
-                else x[n1] = make_float2(ex2_approx(negc2f * d0) * t0, ex2_approx(negc2f * d1) * t1);
+                if (__all_sync(0xffffffffu, dead)) {
+                    x[n1].x = F2(0.f, 0.f);
+                    x[n1].y = F2(0.f, 0.f);
+                } else {
+                    x[n1].x = F2(ex2_approx(nA * d0) * t0, ex2_approx(nB * d0) * t0);
+                    x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
+                }
             }
-            group_transform(x, reinterpret_cast<float2*>(buf), twm, b, grp, kx, out);
+            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.kidx + (size_t)lamA * kNS, out_of(lamA),
+                            p.kidx + (size_t)lamB * kNS, two ? out_of(lamB) : nullptr);
         } else {
             // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
+            const int pos = lb + (slot - npair);
+            const int lam = lam_of(pos);
+            const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
+            const double negc = -cl;
+            const float negc2f = n2f_of(pos);
+            const int cut32 = cut_of(pos);
+            const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
             double2 x[8];
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
@@ -350,7 +375,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
                 }
             }
-            group_transform(x, buf, twr, b, grp, kx, out);
+            group_transform(x, buf, twr, b, grp, p.kidx + (size_t)lam * kNS, out_of(lam));
         }
         base += kGroups;
     }
