@@ -164,14 +164,14 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  *
  * Graded precision of the same pass (the OTF peak is exactly 1, so an entry's size bounds
  * what an error in it can do to the result):
- * PSFR_OPT_EXP_GRADE (default 20): a block of 2 x 160 OTF entries whose every live entry is
+ * PSFR_OPT_EXP_GRADE (default 20): a segment of 2 x 32 OTF entries whose every live entry is
  * below exp(-grade) = 2.1e-9 evaluates exp on the special-function unit in single precision
  * (relative error ~4e-6, i.e. < 1e-14 of the peak per entry); other blocks use the FP64 exp.
  * PSFR_OPT_F32_ROWS (default 25, dim 1280 only): a row pair whose every entry is below
  * exp(-thr) = 1.4e-11 is evaluated AND transformed in single precision; all other rows and
  * the whole column pass are FP64.
  * Measured against the all-FP64 evaluation (tools/diag_grade.py, seven seeing/L0 cases x five
- * wavelengths): largest difference 8e-15 of the PSF peak, 8e-12 pointwise on pixels above
+ * wavelengths): largest difference 1.5e-14 of the PSF peak, 1.1e-11 pointwise on pixels above
  * 1e-6 of the peak - the all-FP64 kernel and numpy differ by 1e-10 there.  A threshold >= the
  * cut disables the respective grade (e.g. 1e30). */
 enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3,
