@@ -112,22 +112,76 @@ def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def checked_ptr(a, count, device, name, writable=False):
+    """Address of a caller-supplied FP64 buffer after checking what the C ABI takes on trust:
+    dtype float64, C-contiguous, at least ``count`` elements, and - for a torch tensor - host
+    memory or the context's own GPU.  ``None`` passes through (optional outputs)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64:
+            raise ValueError('%s must be float64 (got %s)' % (name, a.dtype))
+        if not a.flags['C_CONTIGUOUS']:
+            raise ValueError('%s must be C-contiguous' % name)
+        if writable and not a.flags['WRITEABLE']:
+            raise ValueError('%s is read-only' % name)
+        if a.size < count:
+            raise ValueError('%s holds %d elements, %d are needed' % (name, a.size, count))
+        return a.ctypes.data
+    if hasattr(a, 'data_ptr'):      # torch tensor used purely as a buffer carrier
+        if 'float64' not in str(a.dtype):
+            raise ValueError('%s must be float64 (got %s)' % (name, a.dtype))
+        if not a.is_contiguous():
+            raise ValueError('%s must be contiguous' % name)
+        if a.numel() < count:
+            raise ValueError('%s holds %d elements, %d are needed' % (name, a.numel(), count))
+        dev = a.device
+        if dev.type == 'cuda':
+            if dev.index is not None and dev.index != device:
+                raise ValueError('%s lives on cuda:%d but the context runs on cuda:%d' % (name, dev.index, device))
+        elif dev.type != 'cpu':
+            raise ValueError('%s lives on unsupported device %s' % (name, dev))
+        return a.data_ptr()
+    raise TypeError('%s: unsupported buffer type %r (numpy array or torch tensor expected)' % (name, type(a)))
+
+
 class Context:
-    """One psfr_ctx: twiddles, telescope OTF and workspaces on one GPU."""
+    """One psfr_ctx: twiddles, telescope OTF and workspaces on one GPU.
+
+    The Python object outlives capacity changes: ``ensure`` rebuilds the native context in place
+    (geometry and options are re-applied), so a caller holding a Context never ends up with a
+    dead handle because somebody else asked for more planes."""
 
     def __init__(self, device=0, dim=1280, max_planes=16, max_lambda=35):
-        lib = load()
-        handle = _P()
-        rc = lib.psfr_create(int(device), int(dim), int(max_planes), int(max_lambda), ctypes.byref(handle))
-        if rc != 0:
-            msg = lib.psfr_last_error(None).decode()
-            raise PsfrError(rc, msg)
-        self._h = handle
-        self._lib = lib
+        self._lib = load()
+        self._h = None
+        self._geom = None
+        self._opts = {}
         self.device = int(device)
         self.dim = int(dim)
-        self.max_planes = int(max_planes)
-        self.max_lambda = int(max_lambda)
+        self._create(int(max_planes), int(max_lambda))
+
+    def _create(self, max_planes, max_lambda):
+        handle = _P()
+        rc = self._lib.psfr_create(self.device, self.dim, max_planes, max_lambda, ctypes.byref(handle))
+        if rc != 0:
+            raise PsfrError(rc, self._lib.psfr_last_error(None).decode())
+        self._h = handle
+        self.max_planes = max_planes
+        self.max_lambda = max_lambda
+        if self._geom is not None:
+            self.set_geometry(*self._geom)
+        for key, value in self._opts.items():
+            self._check(self._lib.psfr_set_option(self._h, key, value))
+
+    def ensure(self, max_planes=None, max_lambda=None):
+        """Grow the workspaces (never shrink) so that they hold max_planes x max_lambda."""
+        planes = max(self.max_planes, int(max_planes or 0))
+        lam = max(self.max_lambda, int(max_lambda or 0))
+        if planes != self.max_planes or lam != self.max_lambda or not self._h:
+            self.close()
+            self._create(planes, lam)
+        return self
 
     def close(self):
         if getattr(self, '_h', None):
@@ -144,78 +198,109 @@ class Context:
         if rc != 0:
             raise PsfrError(rc, self._lib.psfr_last_error(self._h).decode())
 
+    def _handle(self):
+        if not self._h:
+            raise PsfrError(E_STATE, 'the context has been closed')
+        return self._h
+
+    def _buf(self, a, count, name, writable=False):
+        return checked_ptr(a, int(count), self.device, name, writable)
+
     # thin wrappers -------------------------------------------------------------------
     def set_geometry(self, f, f_x, f_y):
         f, f_x, f_y = f64(f), f64(f_x), f64(f_y)
-        self._check(self._lib.psfr_set_geometry(self._h, ptr(f), ptr(f_x), ptr(f_y)))
+        n = AO_DIM * AO_DIM
+        self._check(self._lib.psfr_set_geometry(self._handle(), self._buf(f, n, 'f'), self._buf(f_x, n, 'f_x'),
+                                                self._buf(f_y, n, 'f_y')))
+        self._geom = (f, f_x, f_y)
 
     def psd(self, draws, dirs, poslgs, out=None, stream=None):
         draws, dirs, poslgs = f64(draws), f64(dirs), f64(poslgs)
-        self._check(self._lib.psfr_psd(self._h, draws.shape[0], ptr(draws), dirs.shape[1], ptr(dirs),
-                                       poslgs.shape[1], ptr(poslgs), ptr(out), stream))
+        nd, ndir = draws.shape[0], dirs.shape[1]
+        self._check(self._lib.psfr_psd(self._handle(), nd, ptr(draws), ndir, ptr(dirs), poslgs.shape[1], ptr(poslgs),
+                                       self._buf(out, nd * ndir * self.dim * self.dim, 'out', True), stream))
 
     def load_psd(self, psd, nplanes, stream=None):
-        self._check(self._lib.psfr_load_psd(self._h, int(nplanes), ptr(psd), stream))
+        self._check(self._lib.psfr_load_psd(self._handle(), int(nplanes),
+                                            self._buf(psd, int(nplanes) * self.dim * self.dim, 'psd'), stream))
 
     def structure_function(self, nplanes, stream=None):
-        self._check(self._lib.psfr_structure_function(self._h, int(nplanes), stream))
+        self._check(self._lib.psfr_structure_function(self._handle(), int(nplanes), stream))
 
     def psd_to_psf(self, plane, lambda_m, out, stream=None):
-        self._check(self._lib.psfr_psd_to_psf(self._h, int(plane), float(lambda_m), ptr(out), stream))
+        self._check(self._lib.psfr_psd_to_psf(self._handle(), int(plane), float(lambda_m),
+                                              self._buf(out, self.dim * self.dim, 'out', True), stream))
 
     def psf_cube(self, ndraw, ndir, lambda_nm, out, stream=None):
         lam = f64(lambda_nm)
-        self._check(self._lib.psfr_psf_cube(self._h, int(ndraw), int(ndir), lam.size, ptr(lam), ptr(out), stream))
+        self._check(self._lib.psfr_psf_cube(self._handle(), int(ndraw), int(ndir), lam.size, ptr(lam),
+                                            self._buf(out, int(ndraw) * lam.size * PSF_DIM * PSF_DIM, 'out', True), stream))
 
     def convolve(self, ndraw, lambda_nm, alpha_tt, cube, out, stream=None):
         lam, att = f64(lambda_nm), f64(alpha_tt)
-        self._check(self._lib.psfr_convolve(self._h, int(ndraw), lam.size, ptr(lam), ptr(att), ptr(cube),
-                                            ptr(out), stream))
+        n = int(ndraw) * lam.size * PSF_DIM * PSF_DIM
+        if att.size < int(ndraw):
+            raise ValueError('alpha_tt holds %d values for %d draws' % (att.size, ndraw))
+        self._check(self._lib.psfr_convolve(self._handle(), int(ndraw), lam.size, ptr(lam), ptr(att),
+                                            self._buf(cube, n, 'cube'), self._buf(out, n, 'out', True), stream))
 
     def moffat_fit(self, nimg, ny, nx, imgs, params, stream=None):
-        self._check(self._lib.psfr_moffat_fit(self._h, int(nimg), int(ny), int(nx), ptr(imgs), ptr(params), stream))
+        nimg, ny, nx = int(nimg), int(ny), int(nx)
+        self._check(self._lib.psfr_moffat_fit(self._handle(), nimg, ny, nx, self._buf(imgs, nimg * ny * nx, 'imgs'),
+                                              self._buf(params, nimg * FIT_NPAR, 'params', True), stream))
 
     def compute_batch(self, draws, dirs, poslgs, lambda_nm, out_cube=None, out_fit=None, stream=None):
         if not hasattr(draws, 'data_ptr'):      # numpy / sequence; torch tensors pass through as buffers
             draws = f64(draws)
+        if len(draws.shape) != 2 or draws.shape[1] != DRAW_NPAR:
+            raise ValueError('draws must be [ndraw, %d]' % DRAW_NPAR)
         dirs, poslgs, lam = f64(dirs), f64(poslgs), f64(lambda_nm)
-        self._check(self._lib.psfr_compute_batch(self._h, draws.shape[0], ptr(draws), dirs.shape[1], ptr(dirs),
-                                                 poslgs.shape[1], ptr(poslgs), lam.size, ptr(lam),
-                                                 ptr(out_cube), ptr(out_fit), stream))
+        nd = int(draws.shape[0])
+        self._check(self._lib.psfr_compute_batch(
+            self._handle(), nd, self._buf(draws, nd * DRAW_NPAR, 'draws'), dirs.shape[1], ptr(dirs),
+            poslgs.shape[1], ptr(poslgs), lam.size, ptr(lam),
+            self._buf(out_cube, nd * lam.size * PSF_DIM * PSF_DIM, 'out_cube', True),
+            self._buf(out_fit, nd * lam.size * FIT_NPAR, 'out_fit', True), stream))
 
     def mean_refit(self, ncube, nlam, cubes, out_mean=None, out_fit=None, stream=None):
-        self._check(self._lib.psfr_mean_refit(self._h, int(ncube), int(nlam), ptr(cubes), ptr(out_mean),
-                                              ptr(out_fit), stream))
+        ncube, nlam = int(ncube), int(nlam)
+        img = PSF_DIM * PSF_DIM
+        self._check(self._lib.psfr_mean_refit(self._handle(), ncube, nlam, self._buf(cubes, ncube * nlam * img, 'cubes'),
+                                              self._buf(out_mean, nlam * img, 'out_mean', True),
+                                              self._buf(out_fit, nlam * FIT_NPAR, 'out_fit', True), stream))
 
     def polyfit(self, lambda_nm, deg, y, stream=None):
         lam, y = f64(lambda_nm), f64(np.atleast_2d(y))
+        if y.shape[1] != lam.size:
+            raise ValueError('y must hold one value per wavelength')
         coef = np.empty((y.shape[0], deg + 1))
-        self._check(self._lib.psfr_polyfit(self._h, y.shape[0], lam.size, ptr(lam), int(deg), ptr(y), ptr(coef), stream))
+        self._check(self._lib.psfr_polyfit(self._handle(), y.shape[0], lam.size, ptr(lam), int(deg), ptr(y), ptr(coef), stream))
         return coef
 
     def set_option(self, key, value):
-        self._check(self._lib.psfr_set_option(self._h, int(key), float(value)))
+        self._check(self._lib.psfr_set_option(self._handle(), int(key), float(value)))
+        self._opts[int(key)] = float(value)
 
     def get_otf(self):
         out = np.empty((self.dim // 2 + 2, self.dim))
-        self._check(self._lib.psfr_get_otf(self._h, ptr(out)))
+        self._check(self._lib.psfr_get_otf(self._handle(), ptr(out)))
         return out
 
     def get_structure_function(self, plane):
         out = np.empty((self.dim // 2 + 2, self.dim))
-        self._check(self._lib.psfr_get_structure_function(self._h, int(plane), ptr(out)))
+        self._check(self._lib.psfr_get_structure_function(self._handle(), int(plane), ptr(out)))
         return out
 
     def debug_exp(self, x):
         x = f64(x)
         y = np.empty_like(x)
-        self._check(self._lib.psfr_debug_exp(self._h, x.size, ptr(x), ptr(y)))
+        self._check(self._lib.psfr_debug_exp(self._handle(), x.size, ptr(x), ptr(y)))
         return y
 
     def kernel_launches(self):
-        return int(self._lib.psfr_kernel_launches(self._h))
+        return int(self._lib.psfr_kernel_launches(self._handle()))
 
     def last_hot_timing(self):
         ms, n, psfs = _D(), _I(), ctypes.c_longlong()
-        self._check(self._lib.psfr_last_hot_timing(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(psfs)))
+        self._check(self._lib.psfr_last_hot_timing(self._handle(), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(psfs)))
         return ms.value, n.value, psfs.value

@@ -192,7 +192,8 @@ void psfr_destroy(psfr_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     HotTimer* t = timer_of(c);
     if (t) {
-        for (int i = 0; i < 2 * kMaxHotEvents; ++i) cudaEventDestroy(t->ev[i]);
+        for (int i = 0; i < 2 * kMaxHotEvents; ++i)
+            if (t->ev[i]) cudaEventDestroy(t->ev[i]);
         delete t;
     }
     delete c;
@@ -245,9 +246,12 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    if (prop.major < 9)
-        { set_error(nullptr, PSFR_E_UNSUPPORTED, "compute capability %d.%d: sm_100a build", prop.major, prop.minor);
-          psfr_destroy(c); return PSFR_E_UNSUPPORTED; }
+    if (prop.major != 10) {   // the library holds an sm_100a cubin and no PTX
+        set_error(nullptr, PSFR_E_UNSUPPORTED, "device %d has compute capability %d.%d; this library is built for sm_100a (B200) only",
+                  device, prop.major, prop.minor);
+        psfr_destroy(c);
+        return PSFR_E_UNSUPPORTED;
+    }
     const size_t P = max_planes, LM = max_lambda;
     CK(dev_alloc(c, &c->d_tw, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
     CK(dev_alloc(c, &c->d_twc, (size_t)kNB));
@@ -295,8 +299,9 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     c->h_pinned_bytes = 1 << 20;
     CKC(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
     HotTimer* t = new HotTimer();
+    for (int i = 0; i < 2 * kMaxHotEvents; ++i) t->ev[i] = nullptr;
+    c->ev_hot0 = reinterpret_cast<cudaEvent_t>(t);   // owned by the context from here on (psfr_destroy frees it)
     for (int i = 0; i < 2 * kMaxHotEvents; ++i) CKC(cudaEventCreate(&t->ev[i]));
-    c->ev_hot0 = reinterpret_cast<cudaEvent_t>(t);
     std::vector<double2> tw1, tw2;
     build_twiddles<kR3>(tw1, tw2);
     CKC(cudaMemcpy(c->d_tw, tw1.data(), tw1.size() * sizeof(double2), cudaMemcpyHostToDevice));

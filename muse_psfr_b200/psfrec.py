@@ -51,22 +51,20 @@ def _check_dim(dim):
     return int(dim)
 
 
-def get_context(max_planes=None, max_lambda=35, device=None, dim=_DIM):
-    """Context cache: one context per (device, dim), grown when a call needs more capacity."""
+def get_context(max_planes=None, max_lambda=None, device=None, dim=_DIM):
+    """Context cache: one context per (device, dim).  ``max_planes`` / ``max_lambda`` are minimum
+    capacities - ``None`` means "whatever exists" - and a cached context only ever grows, in place
+    (``Context.ensure``): objects handed out earlier stay valid."""
     device = _device() if device is None else int(device)
     dim = _check_dim(dim)
-    if max_planes is None:
-        max_planes = 16 if dim == _DIM else 4
     ctx = _CONTEXTS.get((device, dim))
-    if ctx is None or ctx.max_planes < max_planes or ctx.max_lambda < max_lambda:
-        if ctx is not None:
-            max_planes = max(max_planes, ctx.max_planes)
-            max_lambda = max(max_lambda, ctx.max_lambda)
-            ctx.close()
-        ctx = _lib.Context(device=device, dim=dim, max_planes=max_planes, max_lambda=max_lambda)
-        f, f_x, f_y = ao_frequency_tables()
-        ctx.set_geometry(f, f_x, f_y)
+    if ctx is None:
+        ctx = _lib.Context(device=device, dim=dim, max_planes=max_planes or (16 if dim == _DIM else 4),
+                           max_lambda=max(35, max_lambda or 0))
+        ctx.set_geometry(*ao_frequency_tables())
         _CONTEXTS[(device, dim)] = ctx
+    else:
+        ctx.ensure(max_planes, max_lambda)
     return ctx
 
 

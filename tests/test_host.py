@@ -121,3 +121,32 @@ def test_fit_table_behaves_like_a_table():
     assert tab[1]['SEEING'] == 1.0 and tab[1]['n'] == 2.5
     both = psfrec.FitTable.vstack([tab, tab])
     assert len(both) == 6
+
+
+def test_caller_buffers_are_validated_at_the_binding():
+    """the C ABI trusts pointers; the binding must reject buffers of the wrong dtype,
+    size, layout or device before the library writes through them."""
+    import torch
+    ok = np.empty((2, 3, 40, 40))
+    assert _lib.checked_ptr(ok, 2 * 3 * 1600, 0, 'out_cube', True) == ok.ctypes.data
+    assert _lib.checked_ptr(None, 10, 0, 'out') is None
+    with pytest.raises(ValueError, match='float64'):
+        _lib.checked_ptr(ok.astype(np.float32), 10, 0, 'out_cube', True)
+    with pytest.raises(ValueError, match='elements'):
+        _lib.checked_ptr(ok, ok.size + 1, 0, 'out_cube', True)
+    with pytest.raises(ValueError, match='contiguous'):
+        _lib.checked_ptr(ok[:, :, ::2], 10, 0, 'out_cube', True)
+    ro = ok.copy()
+    ro.flags.writeable = False
+    with pytest.raises(ValueError, match='read-only'):
+        _lib.checked_ptr(ro, 10, 0, 'out_cube', True)
+    t = torch.empty(100, dtype=torch.float64)
+    assert _lib.checked_ptr(t, 100, 0, 'out_fit', True) == t.data_ptr()
+    with pytest.raises(ValueError, match='float64'):
+        _lib.checked_ptr(t.float(), 100, 0, 'out_fit', True)
+    with pytest.raises(ValueError, match='elements'):
+        _lib.checked_ptr(t, 101, 0, 'out_fit', True)
+    with pytest.raises(ValueError, match='contiguous'):
+        _lib.checked_ptr(t[::2], 10, 0, 'out_fit', True)
+    with pytest.raises(TypeError):
+        _lib.checked_ptr([1.0, 2.0], 2, 0, 'out_fit', True)
