@@ -38,7 +38,7 @@ enum {
     PSFR_OK = 0,
     PSFR_E_CUDA = -1,      /* CUDA runtime error (message in psfr_last_error) */
     PSFR_E_ARG = -2,       /* invalid argument */
-    PSFR_E_UNSUPPORTED = -3, /* e.g. dim other than 1280, more than 2 layers (reference: ValueError) */
+    PSFR_E_UNSUPPORTED = -3, /* e.g. dim other than 1280 / 2560, more than PSFR_MAX_LAYERS layers */
     PSFR_E_CAPACITY = -4,  /* batch larger than the context was created for */
     PSFR_E_STATE = -5      /* call order (e.g. geometry not set) */
 };
@@ -49,25 +49,28 @@ enum {
 
 /* Per-draw parameter record (array of doubles, one row per draw).
  * Filled by the host exactly as simul_psd_wfm / convolve_final_psf derive them. */
+#define PSFR_MAX_LAYERS 8    /* the reference works for 1 or 2 layers only (wind directions are a hard-coded
+                              * 2-vector, psfrec.py:66,594); more need explicit wind directions from the host */
 enum {
-    PSFR_DRAW_R0 = 0,        /* r0 at 0.5 um on the line of sight (seeing2r01, psfrec.py:108,183-187) */
+    PSFR_DRAW_R0 = 0,        /* r0 at 0.5 um on the line of sight (seeing2r01, psfrec.py:108,183-187; holds the zenith angle) */
     PSFR_DRAW_L0 = 1,        /* outer scale [m] */
-    PSFR_DRAW_CPHI_0 = 2,    /* 0.0229 (Cn2_l^(-3/5) r0)^(-5/3) per layer (psfrec.py:569-571) */
-    PSFR_DRAW_CPHI_1 = 3,
-    PSFR_DRAW_H_0 = 4,       /* layer altitudes [m] */
-    PSFR_DRAW_H_1 = 5,
-    PSFR_DRAW_WX_0 = 6,      /* wind vector per layer [m/s] (psfrec.py:61,66,594) */
-    PSFR_DRAW_WY_0 = 7,
-    PSFR_DRAW_WX_1 = 8,
-    PSFR_DRAW_WY_1 = 9,
-    PSFR_DRAW_FITC = 10,     /* cst r0^(-5/3) of the fitting PSD (psfrec.py:622-625) */
-    PSFR_DRAW_ALPHA_TT = 11, /* Moffat alpha of the tip-tilt kernel [px] (psfrec.py:881-905) */
-    PSFR_DRAW_NLAYERS = 12,  /* 1 or 2 */
-    PSFR_DRAW_NPAR = 16
+    PSFR_DRAW_FITC = 2,      /* cst r0^(-5/3) of the fitting PSD (psfrec.py:622-625) */
+    PSFR_DRAW_ALPHA_TT = 3,  /* Moffat alpha of the tip-tilt kernel [px] (psfrec.py:881-905) */
+    PSFR_DRAW_NLAYERS = 4,   /* 1 .. PSFR_MAX_LAYERS */
+    PSFR_DRAW_LAYER0 = 8,    /* layer l occupies PSFR_DRAW_LAYER0 + PSFR_LAYER_NPAR * l + PSFR_LAYER_* */
+    PSFR_DRAW_NPAR = 40
+};
+enum {
+    PSFR_LAYER_CPHI = 0,     /* 0.0229 (Cn2_l^(-3/5) r0)^(-5/3) (psfrec.py:569-571) */
+    PSFR_LAYER_H = 1,        /* altitude [m] */
+    PSFR_LAYER_WX = 2,       /* wind vector [m/s] (psfrec.py:61,66,594) */
+    PSFR_LAYER_WY = 3,
+    PSFR_LAYER_NPAR = 4
 };
 
 /* Per-image fit record written by the Moffat fitter (mpdaf Image.moffat_fit columns,
- * psfrec.py:861-871; fwhm still in pixels). */
+ * psfrec.py:861-871; fwhm still in pixels).  The err_* entries are sqrt(|diag((J^T J)^-1)| chi^2/dof), the
+ * estimate scipy.optimize.leastsq's cov_x gives mpdaf. */
 enum {
     PSFR_FIT_PEAK = 0,   /* I */
     PSFR_FIT_Y0 = 1,     /* centre, first (row) axis */
@@ -78,8 +81,10 @@ enum {
     PSFR_FIT_CHISQ = 6,
     PSFR_FIT_ITER = 7,   /* LM iterations used; negative = not converged */
     PSFR_FIT_ERR_PEAK = 8, PSFR_FIT_ERR_Y0 = 9, PSFR_FIT_ERR_X0 = 10,
-    PSFR_FIT_ERR_ALPHA = 11, PSFR_FIT_ERR_N = 12, PSFR_FIT_ERR_FWHM = 13,
-    PSFR_FIT_FLUX = 14,
+    PSFR_FIT_ERR_ALPHA = 11, PSFR_FIT_ERR_N = 12,
+    PSFR_FIT_ERR_FWHM = 13,  /* mpdaf's expression: err_a * n [px] */
+    PSFR_FIT_FLUX = 14,      /* pi a^2 I / (n - 1) */
+    PSFR_FIT_ERR_FLUX = 15,  /* mpdaf's expression err_I err_n err_a^2 err_e with err_e = 0 (circular fit) */
     PSFR_FIT_NPAR = 16
 };
 

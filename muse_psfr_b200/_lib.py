@@ -12,11 +12,18 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpsfr_b200.so')
 
 # record layouts (keep in sync with include/psfr.h)
-DRAW_R0, DRAW_L0, DRAW_CPHI_0, DRAW_CPHI_1, DRAW_H_0, DRAW_H_1 = 0, 1, 2, 3, 4, 5
-DRAW_WX_0, DRAW_WY_0, DRAW_WX_1, DRAW_WY_1, DRAW_FITC, DRAW_ALPHA_TT, DRAW_NLAYERS = 6, 7, 8, 9, 10, 11, 12
-DRAW_NPAR = 16
+DRAW_R0, DRAW_L0, DRAW_FITC, DRAW_ALPHA_TT, DRAW_NLAYERS = 0, 1, 2, 3, 4
+DRAW_LAYER0, DRAW_NPAR = 8, 40
+LAYER_CPHI, LAYER_H, LAYER_WX, LAYER_WY, LAYER_NPAR = 0, 1, 2, 3, 4
+MAX_LAYERS = 8
+
+
+def layer_slot(layer, field):
+    """Index of ``field`` (LAYER_*) of turbulence layer ``layer`` in a draw record."""
+    return DRAW_LAYER0 + LAYER_NPAR * layer + field
+
 FIT_PEAK, FIT_Y0, FIT_X0, FIT_ALPHA, FIT_N, FIT_FWHM, FIT_CHISQ, FIT_ITER = range(8)
-FIT_ERR_PEAK, FIT_ERR_Y0, FIT_ERR_X0, FIT_ERR_ALPHA, FIT_ERR_N, FIT_ERR_FWHM, FIT_FLUX = range(8, 15)
+FIT_ERR_PEAK, FIT_ERR_Y0, FIT_ERR_X0, FIT_ERR_ALPHA, FIT_ERR_N, FIT_ERR_FWHM, FIT_FLUX, FIT_ERR_FLUX = range(8, 16)
 FIT_NPAR = 16
 AO_DIM = 80
 PSF_DIM = 40

@@ -120,7 +120,7 @@ static int small_to_host(Ctx* c, std::vector<double>& dst, const double* src, si
 }
 
 // geometry of a call: directions and guide-star positions; validates the whole draw list once
-// (reference: ValueError for > 2 layers, psfrec.py:66,594).  One host sync at most.
+// (the host keeps the reference's ValueError for > 2 layers without explicit wind directions).  One host sync at most.
 static int upload_geometry(Ctx* c, int ndraw, const double* draws, int ndir, const double* dirs, int ngs,
                            const double* pos, cudaStream_t s) {
     if (ndraw < 1 || ndir < 1) return set_error(c, PSFR_E_ARG, "ndraw=%d ndir=%d", ndraw, ndir);
@@ -136,8 +136,8 @@ static int upload_geometry(Ctx* c, int ndraw, const double* draws, int ndir, con
     if (rc) return rc;
     for (int d = 0; d < ndraw; ++d) {
         const double nl = h[(size_t)d * PSFR_DRAW_NPAR + PSFR_DRAW_NLAYERS];
-        if (!(nl == 1.0 || nl == 2.0))
-            return set_error(c, PSFR_E_UNSUPPORTED, "draw %d has %g layers; the reference supports 1 or 2", d, nl);
+        if (!(nl >= 1.0 && nl <= (double)PSFR_MAX_LAYERS && nl == std::floor(nl)))
+            return set_error(c, PSFR_E_UNSUPPORTED, "draw %d has %g layers; 1 to %d are supported", d, nl, PSFR_MAX_LAYERS);
     }
     return PSFR_OK;
 }

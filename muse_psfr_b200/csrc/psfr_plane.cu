@@ -419,13 +419,15 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
             o[PSFR_FIT_ERR_X0] = e[2];
             o[PSFR_FIT_ERR_ALPHA] = e[3];
             o[PSFR_FIT_ERR_N] = e[4];
-            const double dk = -pow(2.0, 1.0 / n) * log(2.0) / (n * n * sqrt(pow(2.0, 1.0 / n) - 1.0));
-            o[PSFR_FIT_ERR_FWHM] = sqrt((kf * e[3]) * (kf * e[3]) + (a * dk * e[4]) * (a * dk * e[4]));
+            // mpdaf Image.moffat_fit (fit_n, circular): err_fwhm = err_a * n; err_flux = err_I err_n err_a^2 err_e
+            // with err_e = 0 for a circular fit (restated from mpdaf 3.x; the package is not in the reference tree)
+            o[PSFR_FIT_ERR_FWHM] = e[3] * n;
+            o[PSFR_FIT_ERR_FLUX] = e[0] * e[4] * e[3] * e[3] * 0.0;
         } else {
             for (int i = PSFR_FIT_ERR_PEAK; i <= PSFR_FIT_ERR_FWHM; ++i) o[i] = nan("");
+            o[PSFR_FIT_ERR_FLUX] = nan("");
         }
-        o[PSFR_FIT_FLUX] = 3.141592653589793 * a * a * x[0] / (n - 1.0);
-        o[15] = 0.0;
+        o[PSFR_FIT_FLUX] = x[0] / (n - 1.0) * (3.141592653589793 * a * a);
     }
     __syncwarp();
     }   // next image

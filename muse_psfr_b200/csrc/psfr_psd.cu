@@ -91,8 +91,9 @@ __global__ void ao_zone_kernel(PsdParams p) {
     const double vk = pow_m11_6(f * f + (1 / L0) * (1 / L0));
     double err_rec = 0.0;
     for (int l = 0; l < nl; ++l) {
-        const double h = dr[PSFR_DRAW_H_0 + l];
-        const double wx = dr[PSFR_DRAW_WX_0 + 2 * l], wy = dr[PSFR_DRAW_WY_0 + 2 * l];
+        const double* ly = dr + PSFR_DRAW_LAYER0 + PSFR_LAYER_NPAR * l;
+        const double h = ly[PSFR_LAYER_H];
+        const double wx = ly[PSFR_LAYER_WX], wy = ly[PSFR_LAYER_WY];
         const double lag = np_sinc(wx * ti * fx + wy * ti * fy);
         cd acc = {0.0, 0.0};
         for (int j = 0; j < ngs; ++j) {
@@ -108,7 +109,7 @@ __global__ void ao_zone_kernel(PsdParams p) {
         }
         const cd pb = cexp_i(2 * pi * (h * 60 / 206265 * bf - (wx * dT * fx + wy * dT * fy)));
         const double prx = pb.x - acc.x, pry = pb.y - acc.y;
-        err_rec += (prx * prx + pry * pry) * (dr[PSFR_DRAW_CPHI_0 + l] * vk);
+        err_rec += (prx * prx + pry * pry) * (ly[PSFR_LAYER_CPHI] * vk);
     }
     double dsp = err_rec + err_noise;
     if (cell == 0) dsp = 0.0;

@@ -143,7 +143,26 @@ def tiptilt_alpha(seeing, GL, L0):
     return fwhmTTopt / (2 * np.sqrt(2 ** (1. / beta_tt) - 1))
 
 
-def draw_record(Cn2, h, seeing, L0, zenith=0., alpha_tt=1.0):
+def _wind_vectors(h_arr, wind_dir):
+    """Wind vector per layer [2, nl]: 12.5 m/s (12 for integer altitudes, as ``np.full_like(h, 12.5)``
+    does in the reference, psfrec.py:60-61) along the reference's two hard-coded directions
+    (psfrec.py:66) or along ``wind_dir`` [rad] - required beyond two layers, where the reference
+    itself fails (ValueError from broadcasting at psfrec.py:594)."""
+    nl = h_arr.shape[-1]
+    if wind_dir is None:
+        if nl > 2:
+            raise ValueError('operands could not be broadcast together: the reference has wind directions for '
+                             '2 layers only; pass wind_dir= (one angle [rad] per layer) for more')
+        arg_v = _WIND_DIR[:nl]
+    else:
+        arg_v = np.asarray(wind_dir, dtype=float)
+        if arg_v.shape != (nl,):
+            raise ValueError('wind_dir must hold one angle [rad] per layer')
+    vent = np.full_like(h_arr, 12.5)
+    return np.stack([vent * np.cos(arg_v), vent * np.sin(arg_v)])
+
+
+def draw_record(Cn2, h, seeing, L0, zenith=0., alpha_tt=1.0, wind_dir=None):
     """Per-draw constants of simul_psd_wfm / dsp4muse / psd_fit, evaluated with the
     reference's own scalar expressions (psfrec.py:57-66, 108, 569-571, 594, 622-625)."""
     Cn2 = np.array(Cn2, dtype=float)
@@ -151,12 +170,9 @@ def draw_record(Cn2, h, seeing, L0, zenith=0., alpha_tt=1.0):
     h_arr = np.array(h)
     if h_arr.ndim != 1 or h_arr.size != Cn2.size:
         raise ValueError('Cn2 and h must be 1-D sequences of the same length')
-    if h_arr.size > 2:
-        # the reference's wind directions are a hard-coded 2-vector (psfrec.py:66, 594)
-        raise ValueError('operands could not be broadcast together: at most 2 layers are supported')
-    vent = np.full_like(h_arr, 12.5)              # integer h -> 12 m/s, as the reference
-    arg_v = _WIND_DIR[:h_arr.size]
-    wind = np.stack([vent * np.cos(arg_v), vent * np.sin(arg_v)])
+    if h_arr.size > _lib.MAX_LAYERS:
+        raise ValueError('at most %d turbulence layers are supported' % _lib.MAX_LAYERS)
+    wind = _wind_vectors(h_arr, wind_dir)
     r0ref = seeing2r01(seeing, 0.5, zenith)
     rec = np.zeros(_lib.DRAW_NPAR)
     rec[_lib.DRAW_R0] = r0ref
@@ -164,42 +180,45 @@ def draw_record(Cn2, h, seeing, L0, zenith=0., alpha_tt=1.0):
     cst = ((gamma(11 / 6) ** 2 / (2 * np.pi ** (11 / 3))) * (24 * gamma(6 / 5) / 5) ** (5 / 6))
     rec[_lib.DRAW_FITC] = cst * r0ref ** (-5 / 3)
     for l in range(h_arr.size):
-        rec[_lib.DRAW_CPHI_0 + l] = 0.0229 * (Cn2[l] ** (-3 / 5) * r0ref) ** (-5 / 3)
-        rec[_lib.DRAW_H_0 + l] = float(h_arr[l])
-        rec[_lib.DRAW_WX_0 + 2 * l] = wind[0, l]
-        rec[_lib.DRAW_WY_0 + 2 * l] = wind[1, l]
+        rec[_lib.layer_slot(l, _lib.LAYER_CPHI)] = 0.0229 * (Cn2[l] ** (-3 / 5) * r0ref) ** (-5 / 3)
+        rec[_lib.layer_slot(l, _lib.LAYER_H)] = float(h_arr[l])
+        rec[_lib.layer_slot(l, _lib.LAYER_WX)] = wind[0, l]
+        rec[_lib.layer_slot(l, _lib.LAYER_WY)] = wind[1, l]
     rec[_lib.DRAW_ALPHA_TT] = alpha_tt
     rec[_lib.DRAW_NLAYERS] = h_arr.size
     return rec
 
 
-def draw_records(seeing, GL, L0, h=(100, 10000)):
-    """Vectorised ``draw_record`` for compute_psf's two-layer profile Cn2 = [GL, 1 - GL]
-    (psfrec.py:953); ``h`` is one pair or an array [ndraw, 2].  Same expressions as the
-    scalar version evaluated with numpy's array kernels, which may differ from libm's
-    scalar pow() by a few ulp (measured <= 3 ulp on the pow chains)."""
+def draw_records(seeing, GL, L0, h=(100, 10000), zenith=0., Cn2=None, wind_dir=None):
+    """Vectorised ``draw_record``.  Default profile: compute_psf's two layers Cn2 = [GL, 1 - GL]
+    (psfrec.py:953); ``Cn2`` ([nl] or [ndraw, nl]) replaces it.  ``h`` is one altitude per layer or an
+    array [ndraw, nl].  Same expressions as the scalar version evaluated with numpy's array kernels,
+    which may differ from libm's scalar pow() by a few ulp (measured <= 3 ulp on the pow chains)."""
     seeing, GL, L0 = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (seeing, GL, L0))
     nd = seeing.size
     h_arr = np.array(h)
-    if h_arr.shape[-1] != 2 or h_arr.ndim > 2:
-        raise ValueError('operands could not be broadcast together: h must hold 2 layer altitudes')
-    vent = np.full_like(h_arr, 12.5)             # integer altitudes -> 12 m/s, as the reference
-    wx, wy = vent * np.cos(_WIND_DIR), vent * np.sin(_WIND_DIR)
-    cn2 = np.stack([GL, 1 - GL], axis=1)
+    cn2 = np.stack([GL, 1 - GL], axis=1) if Cn2 is None else np.broadcast_to(np.asarray(Cn2, dtype=float),
+                                                                               (nd, np.shape(Cn2)[-1]))
+    nl = cn2.shape[1]
+    if h_arr.shape[-1] != nl or h_arr.ndim > 2:
+        raise ValueError('operands could not be broadcast together: h must hold %d layer altitudes' % nl)
+    if nl > _lib.MAX_LAYERS:
+        raise ValueError('at most %d turbulence layers are supported' % _lib.MAX_LAYERS)
+    wx, wy = _wind_vectors(h_arr, wind_dir)
     cn2 = cn2 / cn2.sum(axis=1)[:, None]
-    r0ref = seeing2r01(seeing, 0.5, 0.)
+    r0ref = seeing2r01(seeing, 0.5, zenith)
     cst = ((gamma(11 / 6) ** 2 / (2 * np.pi ** (11 / 3))) * (24 * gamma(6 / 5) / 5) ** (5 / 6))
     recs = np.zeros((nd, _lib.DRAW_NPAR))
     recs[:, _lib.DRAW_R0] = r0ref
     recs[:, _lib.DRAW_L0] = L0
     recs[:, _lib.DRAW_FITC] = cst * r0ref ** (-5 / 3)
-    for l in range(2):
-        recs[:, _lib.DRAW_CPHI_0 + l] = 0.0229 * (cn2[:, l] ** (-3 / 5) * r0ref) ** (-5 / 3)
-        recs[:, _lib.DRAW_H_0 + l] = h_arr[..., l]
-        recs[:, _lib.DRAW_WX_0 + 2 * l] = wx[..., l]
-        recs[:, _lib.DRAW_WY_0 + 2 * l] = wy[..., l]
+    for l in range(nl):
+        recs[:, _lib.layer_slot(l, _lib.LAYER_CPHI)] = 0.0229 * (cn2[:, l] ** (-3 / 5) * r0ref) ** (-5 / 3)
+        recs[:, _lib.layer_slot(l, _lib.LAYER_H)] = h_arr[..., l]
+        recs[:, _lib.layer_slot(l, _lib.LAYER_WX)] = wx[..., l]
+        recs[:, _lib.layer_slot(l, _lib.LAYER_WY)] = wy[..., l]
     recs[:, _lib.DRAW_ALPHA_TT] = tiptilt_alpha(seeing, GL, L0)
-    recs[:, _lib.DRAW_NLAYERS] = 2
+    recs[:, _lib.DRAW_NLAYERS] = nl
     return recs
 
 
@@ -243,8 +262,17 @@ class FitTable:
 
 
 def _table_from_fit(lbda, fit, pixscale=0.2):
+    """Columns of the reference's fit table (psfrec.py:866-870: mpdaf Moffat2D attributes minus
+    ima / rot / cont / err_rot / err_cont, fwhm and err_fwhm x 0.2) plus ``converged``, an extension:
+    0 where the Levenberg-Marquardt iteration ran out of steps (PSFR_FIT_ITER < 0); such rows are
+    also reported by a warning on the module logger."""
     fwhm = fit[:, _lib.FIT_FWHM] * pixscale
     efw = fit[:, _lib.FIT_ERR_FWHM] * pixscale
+    converged = fit[:, _lib.FIT_ITER] > 0
+    if not converged.all():
+        bad = np.flatnonzero(~converged)
+        logger.warning('Moffat fit did not converge for %d of %d images (first at index %d)',
+                       bad.size, len(fit), bad[0])
     return FitTable({
         'lbda': np.asarray(lbda, dtype=float),
         'center': fit[:, [_lib.FIT_Y0, _lib.FIT_X0]].copy(),
@@ -253,22 +281,25 @@ def _table_from_fit(lbda, fit, pixscale=0.2):
         'n': fit[:, _lib.FIT_N].copy(),
         'peak': fit[:, _lib.FIT_PEAK].copy(),
         'err_center': fit[:, [_lib.FIT_ERR_Y0, _lib.FIT_ERR_X0]].copy(),
-        'err_flux': np.full(len(fit), np.nan),
+        'err_flux': fit[:, _lib.FIT_ERR_FLUX].copy(),
         'err_fwhm': np.stack([efw, efw], axis=1),
         'err_n': fit[:, _lib.FIT_ERR_N].copy(),
         'err_peak': fit[:, _lib.FIT_ERR_PEAK].copy(),
+        'converged': converged.astype(np.int64),
     })
 
 
 # --------------------------------------------------------------------------- reference API
 def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., plot=False, npsflin=1, dim=1280,
-                  three_lgs_mode=False, verbose=True):
+                  three_lgs_mode=False, verbose=True, wind_dir=None):
     """Residual-phase PSD per field direction, [npsflin**2, dim, dim] in nm^2
-    (psfrec.py:36-151), synthesised on the GPU."""
+    (psfrec.py:36-151), synthesised on the GPU.  Extension: up to 8 layers when ``wind_dir`` gives
+    one wind direction [rad] per layer (without it more than 2 layers raise ValueError, as the
+    reference does)."""
     dim = _check_dim(dim)
     if three_lgs_mode and verbose:
         logger.info('Using three lasers mode')
-    rec = draw_record(Cn2, h, seeing, L0, zenith)
+    rec = draw_record(Cn2, h, seeing, L0, zenith, wind_dir=wind_dir)
     dirs = direction_perf(npsflin)
     ctx = get_context(max_planes=max(16 if dim == _DIM else 4, dirs.shape[1]), dim=dim)
     out = np.empty((dirs.shape[1], dim, dim))
@@ -367,16 +398,19 @@ def fit_psf_cube(lbda, psfcube):
 
 
 def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, verbose=True,
-                dim=_DIM):
+                dim=_DIM, zenith=0., Cn2=None, wind_dir=None):
     """Reconstruct a PSF from seeing, GL and L0 (psfrec.py:933-978): returns (table, psf).
-    ``dim`` (1280, the reference's hard-coded grid, or 2560) is an extension of this backend."""
+    Extensions of this backend (the reference hard-codes them, psfrec.py:953-955): ``dim`` (1280 or
+    2560), ``zenith`` [deg], and a turbulence profile ``Cn2`` / ``h`` / ``wind_dir`` of up to 8 layers
+    in place of [GL, 1 - GL] (GL still sets the tip-tilt kernel, psfrec.py:881)."""
     if verbose:
         logger.info('Compute PSF with seeing=%.2f GL=%.2f L0=%.2f', seeing, GL, L0)
         if three_lgs_mode:
             logger.info('Using three lasers mode')
     lam = np.atleast_1d(np.asarray(lbda, dtype=float))
     fit, cube = compute_psf_batch(lam, [seeing], [GL], [L0], npsflin=npsflin, h=h,
-                                  three_lgs_mode=three_lgs_mode, dim=dim)
+                                  three_lgs_mode=three_lgs_mode, dim=dim, zenith=zenith, Cn2=Cn2,
+                                  wind_dir=wind_dir)
     res = _table_from_fit(lam, fit[0])
     res.meta.update({'SEEING': seeing, 'GL': GL, 'L0': L0})
     res['SEEING'] = seeing
@@ -390,7 +424,7 @@ reconstruct_psf = compute_psf   # pre-1.0 name used by BASELINE.json's north_sta
 
 def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False,
                       out_cube=None, out_fit=None, want_cube=True, device=None, max_planes=None, stream=None,
-                      dim=_DIM):
+                      dim=_DIM, zenith=0., Cn2=None, wind_dir=None):
     """Batched ``compute_psf``: one fused device pipeline for many (seeing, GL, L0[, h]) draws.
 
     ``h`` is one (h0, h1) pair or an array [ndraw, 2].  Returns (fit [ndraw, nl, FIT_NPAR],
@@ -402,11 +436,13 @@ def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs
     if nd <= 64:
         # scalar expressions, bit-identical to the reference's own scalars
         h_arr = np.array(h)
-        recs = np.stack([draw_record([GL[i], 1 - GL[i]], h_arr[i] if h_arr.ndim == 2 else h_arr, seeing[i],
-                                     L0[i], 0., alpha_tt=tiptilt_alpha(seeing[i], GL[i], L0[i]))
+        prof = None if Cn2 is None else np.asarray(Cn2, dtype=float)
+        recs = np.stack([draw_record([GL[i], 1 - GL[i]] if prof is None else (prof[i] if prof.ndim == 2 else prof),
+                                     h_arr[i] if h_arr.ndim == 2 else h_arr, seeing[i], L0[i], zenith,
+                                     alpha_tt=tiptilt_alpha(seeing[i], GL[i], L0[i]), wind_dir=wind_dir)
                          for i in range(nd)])
     else:
-        recs = draw_records(seeing, GL, L0, h)
+        recs = draw_records(seeing, GL, L0, h, zenith=zenith, Cn2=Cn2, wind_dir=wind_dir)
     dirs = direction_perf(npsflin)
     dim = _check_dim(dim)
     if max_planes is None:

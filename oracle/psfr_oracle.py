@@ -162,7 +162,7 @@ def wind_speed_for(h):
     return np.full_like(np.array(h), WIND_SPEED).astype(float)
 
 
-def dsp4muse(Cn2, h, L0, r0ref, pos_arcsec, dir_arcsec, h_recons=ALT_DM, vent=None):
+def dsp4muse(Cn2, h, L0, r0ref, pos_arcsec, dir_arcsec, h_recons=ALT_DM, vent=None, wind_dir=None):
     """AO-zone PSD cube [ndir, 80, 80] (unshifted frequency order, transposed as the
     reference does at the end), psfrec.py:531-613."""
     f, _, f_x, f_y = ao_frequency_tables()
@@ -170,8 +170,11 @@ def dsp4muse(Cn2, h, L0, r0ref, pos_arcsec, dir_arcsec, h_recons=ALT_DM, vent=No
     dirs = dir_arcsec / 60
     Cn2 = np.atleast_1d(np.asarray(Cn2, dtype=float))
     h = np.atleast_1d(np.asarray(h, dtype=float))
-    if h.size > 2:
-        raise ValueError('the reference supports at most 2 layers (psfrec.py:66,594)')
+    if wind_dir is None:
+        if h.size > 2:
+            raise ValueError('the reference supports at most 2 layers (psfrec.py:66,594)')
+        wind_dir = WIND_DIR[:h.size]
+    wind_dir = np.asarray(wind_dir, dtype=float)      # extension: one direction per layer
     layer_psd = (0.0229 * (Cn2[:, None, None] ** (-3 / 5) * r0ref) ** (-5 / 3) *
                  (f ** 2 + (1 / L0) ** 2) ** (-11 / 6))                        # :569-571
     ngs = pos.shape[1]
@@ -181,7 +184,7 @@ def dsp4muse(Cn2, h, L0, r0ref, pos_arcsec, dir_arcsec, h_recons=ALT_DM, vent=No
     td = DELAY_MS * 1e-3
     if vent is None:
         vent = np.full_like(h, WIND_SPEED)
-    wind = np.stack([vent * np.cos(WIND_DIR[:h.size]), vent * np.sin(WIND_DIR[:h.size])])
+    wind = np.stack([vent * np.cos(wind_dir), vent * np.sin(wind_dir)])
     W = glao_reconstructor(f, f_x, f_y, pitch, pos, sig2, h_recons)
     out = np.empty((dirs.shape[1],) + f.shape)
     for b in range(dirs.shape[1]):
@@ -203,8 +206,9 @@ def psd_fit(dim, L, r0, L0, fc):
     return out
 
 
-def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., npsflin=1, dim=1280, three_lgs_mode=False):
-    """Residual-phase PSD [ndir, dim, dim] in nm^2, psfrec.py:36-151."""
+def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., npsflin=1, dim=1280, three_lgs_mode=False, wind_dir=None):
+    """Residual-phase PSD [ndir, dim, dim] in nm^2, psfrec.py:36-151.  ``wind_dir`` (one angle per
+    layer) lifts the reference's two-layer limit; the formulas are the reference's for any layer count."""
     Cn2 = np.array(Cn2, dtype=float)
     Cn2 = Cn2 / Cn2.sum()
     vent = wind_speed_for(h)
@@ -213,7 +217,7 @@ def simul_psd_wfm(Cn2, h, seeing, L0, zenith=0., npsflin=1, dim=1280, three_lgs_
     dirs = direction_perf(npsflin)
     r0ref = seeing2r01(seeing, LAMBDA_REF_UM, zenith)
     fc = 1 / (2 * (D_PUP / N_ACT))
-    ao = dsp4muse(Cn2, h, L0, r0ref, pos, dirs, vent=vent)
+    ao = dsp4muse(Cn2, h, L0, r0ref, pos, dirs, vent=vent, wind_dir=wind_dir)
     fit = psd_fit(dim, 2 * D_PUP, r0ref, L0, fc)
     psd = np.repeat(fit[None], ao.shape[0], axis=0)
     sl = slice(dim // 2 - DIM_PUP, dim // 2 + DIM_PUP)
@@ -382,11 +386,14 @@ def moffat_fit(img):
     n = v[4]
     k = 2 * np.sqrt(2 ** (1 / n) - 1)
     fwhm = a * k
-    # error propagation for fwhm = a*k(n)
-    dk_dn = -(2 ** (1 / n)) * np.log(2) / (n ** 2 * np.sqrt(2 ** (1 / n) - 1))
-    err_fwhm = np.sqrt((k * err[3]) ** 2 + (a * dk_dn * err[4]) ** 2)
+    # Derived columns as mpdaf's Image.moffat_fit forms them for fit_n=True, circular=True (mpdaf 3.x,
+    # mpdaf/obj/image.py, restated from the published source - the package is neither in the reference
+    # tree nor installable here, so these columns are PARITY UNPINNED): e = 1, err_e = 0,
+    #   flux = I / (n - 1) * (pi a^2 e),  err_fwhm = err_a * n,  err_flux = err_I err_n err_a^2 err_e (= 0).
+    err_fwhm = err[3] * n
+    err_flux = err[0] * err[4] * err[3] * err[3] * 0.0
     return dict(v=v, center=np.array([v[1], v[2]]), fwhm=fwhm, n=n, peak=v[0],
-                flux=np.pi * a * a * v[0] / (n - 1), chisq=chisq,
+                flux=v[0] / (n - 1) * (np.pi * a * a), chisq=chisq, err_a=err[3], err_flux=err_flux,
                 err_center=err[1:3], err_n=err[4], err_peak=err[0], err_fwhm=err_fwhm)
 
 
@@ -400,14 +407,21 @@ def fit_psf_cube(lbda, cube, pixscale=0.2):
                 n=np.array([f['n'] for f in fits]),
                 peak=np.array([f['peak'] for f in fits]),
                 flux=np.array([f['flux'] for f in fits]),
+                err_center=np.array([f['err_center'] for f in fits]),
+                err_flux=np.array([f['err_flux'] for f in fits]),
+                err_fwhm=np.array([f['err_fwhm'] for f in fits]) * pixscale,
+                err_n=np.array([f['err_n'] for f in fits]),
+                err_peak=np.array([f['err_peak'] for f in fits]),
                 chisq=np.array([f['chisq'] for f in fits]))
 
 
-def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, dim=1280):
-    """Per-draw driver, psfrec.py:933-978 (returns (fit dict, psf[nl,40,40]))."""
+def compute_psf(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False, dim=1280,
+                zenith=0., Cn2=None, wind_dir=None):
+    """Per-draw driver, psfrec.py:933-978 (returns (fit dict, psf[nl,40,40])); zenith / Cn2 / wind_dir
+    are the extensions of SURVEY 8(f4) (the reference fixes zenith = 0 and Cn2 = [GL, 1 - GL])."""
     lbda = np.atleast_1d(np.asarray(lbda, dtype=float))
-    psd = simul_psd_wfm([GL, 1 - GL], h, seeing, L0, zenith=0., npsflin=npsflin,
-                        dim=dim, three_lgs_mode=three_lgs_mode)
+    psd = simul_psd_wfm([GL, 1 - GL] if Cn2 is None else Cn2, h, seeing, L0, zenith=zenith, npsflin=npsflin,
+                        dim=dim, three_lgs_mode=three_lgs_mode, wind_dir=wind_dir)
     psf = psf_muse(psd[0] if npsflin == 1 else psd, lbda)
     psf = convolve_final_psf(lbda, seeing, GL, L0, psf)
     res = fit_psf_cube(lbda, psf)

@@ -88,6 +88,28 @@ def test_three_layers_rejected(psfrec):
         psfrec.simul_psd_wfm([0.5, 0.3, 0.2], (100, 5000, 10000), 1.0, 25.)
 
 
+def test_more_layers_and_zenith(psfrec):
+    """layers beyond the reference's two (explicit wind directions) and zenith != 0,
+    against the oracle extended the same way (the reference's formulas are layer-count agnostic)."""
+    cn2, h, wd = [0.5, 0.3, 0.15, 0.05], (80., 2500., 9000., 14000.), [0.628163, -0.326497, 1.2, -2.0]
+    got = psfrec.simul_psd_wfm(cn2, h, 0.9, 18., zenith=30., npsflin=2, wind_dir=wd)
+    ref = orc.simul_psd_wfm(cn2, h, 0.9, 18., zenith=30., npsflin=2, wind_dir=wd)
+    assert np.array_equal(got == 0, ref == 0)
+    assert_allclose(got, ref, rtol=1e-10, atol=0)
+    lam = np.array([490., 700., 930.])
+    tab, cube = psfrec.compute_psf(lam, 0.9, 0.6, 18., h=h[:3], Cn2=cn2[:3], wind_dir=wd[:3], zenith=30., verbose=False)
+    rtab, rcube = orc.compute_psf(lam, 0.9, 0.6, 18., h=h[:3], Cn2=cn2[:3], wind_dir=wd[:3], zenith=30.)
+    for i in range(lam.size):
+        assert_image_close(cube[i], rcube[i])
+    assert_allclose(tab['fwhm'][:, 0], rtab['fwhm'], rtol=FIT_RTOL)
+    assert_allclose(tab['n'], rtab['n'], rtol=FIT_RTOL)
+    # zenith alone on the reference's own two-layer profile
+    tab0, cube0 = psfrec.compute_psf(lam[:1], 1.0, 0.7, 25., zenith=30., verbose=False)
+    rtab0, rcube0 = orc.compute_psf(lam[:1], 1.0, 0.7, 25., zenith=30.)
+    assert_image_close(cube0[0], rcube0[0])
+    assert_allclose(tab0['fwhm'][:, 0], rtab0['fwhm'], rtol=FIT_RTOL)
+
+
 # ---------------------------------------------------------------- BASELINE config 5: dim = 2560
 @pytest.fixture(scope='module')
 def psd5(psfrec):
@@ -349,6 +371,38 @@ def test_fit_psf_cube(psfrec, golden):
     assert_allclose(tab['lbda'], LBDA35)
 
 
+def test_fit_table_every_column(psfrec, golden):
+    """flux, peak and every err_* column against the oracle's restatement of mpdaf's
+    Image.moffat_fit on the same images (errors: rtol 1e-4 - the oracle's covariance comes from
+    MINPACK's finite-difference Jacobian, the kernel's from the analytic one)."""
+    go = golden('oracle_config1')
+    sel = [0, 9, 17, 26, 34]
+    tab = psfrec.fit_psf_cube(LBDA35[sel], go['conv'][sel])
+    ref = orc.fit_psf_cube(LBDA35[sel], go['conv'][sel])
+    assert tab.colnames == ['lbda', 'center', 'flux', 'fwhm', 'n', 'peak', 'err_center', 'err_flux', 'err_fwhm',
+                            'err_n', 'err_peak', 'converged']
+    assert_allclose(tab['flux'], ref['flux'], rtol=FIT_RTOL)
+    assert_allclose(tab['peak'], ref['peak'], rtol=FIT_RTOL)
+    assert_allclose(tab['err_center'], ref['err_center'], rtol=1e-4)
+    assert_allclose(tab['err_n'], ref['err_n'], rtol=1e-4)
+    assert_allclose(tab['err_peak'], ref['err_peak'], rtol=1e-4)
+    assert_allclose(tab['err_fwhm'][:, 0], ref['err_fwhm'], rtol=1e-4)
+    assert np.array_equal(tab['err_fwhm'][:, 0], tab['err_fwhm'][:, 1])
+    assert np.array_equal(tab['err_flux'], ref['err_flux'])          # mpdaf: err_e = 0 for a circular fit
+    assert tab['converged'].all()
+    assert (ref['err_n'] > 0).all() and (ref['err_fwhm'] > 0).all()
+
+
+def test_non_converged_fit_is_reported(psfrec, caplog):
+    """A fit that runs out of iterations is flagged in the table and logged, not returned silently."""
+    import logging
+    img = np.zeros((1, 40, 40))          # no minimum: every parameter is degenerate
+    with caplog.at_level(logging.WARNING, logger='muse_psfr.psfrec'):
+        tab = psfrec.fit_psf_cube([500.], img)
+    assert tab['converged'][0] == 0
+    assert any('did not converge' in r.message for r in caplog.records)
+
+
 def test_fit_exact_moffat_known_answer(psfrec):
     """Idempotence: images that ARE Moffat profiles return their own parameters."""
     p, q = np.mgrid[:40, :40].astype(float)
@@ -496,7 +550,7 @@ def test_c_abi_argument_errors(psfrec):
     ctx = psfrec.get_context()
     lib = _lib.load()
     recs = np.zeros((1, _lib.DRAW_NPAR))
-    recs[0, _lib.DRAW_NLAYERS] = 3                       # the reference raises ValueError for 3 layers
+    recs[0, _lib.DRAW_NLAYERS] = _lib.MAX_LAYERS + 1      # more layers than the record holds
     dirs, pos, lam = _lib.f64(psfrec.direction_perf(1)), _lib.f64(psfrec._lgs_positions(False)), np.array([500.])
     out = np.empty((1, 1, 40, 40))
     rc = lib.psfr_compute_batch(ctx._h, 1, _lib.ptr(recs), 1, _lib.ptr(dirs), 4, _lib.ptr(pos), 1, _lib.ptr(lam),

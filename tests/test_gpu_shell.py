@@ -112,7 +112,7 @@ def test_script_with_file(pkg, tmp_path):                       # test_psfrec.py
         assert hdul['PSF_MEAN'].data.shape == (3, 40, 40)
         assert hdul['FIT_ROWS'].data.dtype.names == (
             'lbda', 'center', 'flux', 'fwhm', 'n', 'peak', 'err_center', 'err_flux', 'err_fwhm', 'err_n',
-            'err_peak', 'SEEING', 'GL', 'L0', 'row_idx', 'lgs_idx')
+            'err_peak', 'converged', 'SEEING', 'GL', 'L0', 'row_idx', 'lgs_idx')
     with open(logfile) as f:
         lines = f.read().splitlines()
     assert lines[2:] == [

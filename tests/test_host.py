@@ -26,10 +26,15 @@ def test_header_and_binding_agree():
     declared = set(re.findall(r'PSFR_API\s+[\w\s\*]+?\b(psfr_\w+)\s*\(', hdr))
     assert declared == set(_lib.exported_symbols())
     # record layouts
-    for name in ('R0', 'L0', 'CPHI_0', 'H_0', 'WX_0', 'WY_1', 'FITC', 'ALPHA_TT', 'NLAYERS', 'NPAR'):
+    for name in ('R0', 'L0', 'FITC', 'ALPHA_TT', 'NLAYERS', 'LAYER0', 'NPAR'):
         m = re.search(r'PSFR_DRAW_%s = (\d+)' % name, hdr)
         assert int(m.group(1)) == getattr(_lib, 'DRAW_' + name)
-    for name in ('PEAK', 'Y0', 'X0', 'ALPHA', 'N', 'FWHM', 'CHISQ', 'ITER', 'ERR_FWHM', 'FLUX', 'NPAR'):
+    for name in ('CPHI', 'H', 'WX', 'WY', 'NPAR'):
+        m = re.search(r'PSFR_LAYER_%s = (\d+)' % name, hdr)
+        assert int(m.group(1)) == getattr(_lib, 'LAYER_' + name)
+    assert int(re.search(r'#define PSFR_MAX_LAYERS (\d+)', hdr).group(1)) == _lib.MAX_LAYERS
+    assert _lib.layer_slot(_lib.MAX_LAYERS - 1, _lib.LAYER_WY) < _lib.DRAW_NPAR
+    for name in ('PEAK', 'Y0', 'X0', 'ALPHA', 'N', 'FWHM', 'CHISQ', 'ITER', 'ERR_FWHM', 'FLUX', 'ERR_FLUX', 'NPAR'):
         m = re.search(r'PSFR_FIT_%s = (\d+)' % name, hdr)
         assert int(m.group(1)) == getattr(_lib, 'FIT_' + name)
     # option keys of psfr_set_option
@@ -72,15 +77,21 @@ def test_draw_record_matches_reference_scalars():
     assert rec[_lib.DRAW_R0] == r0
     assert rec[_lib.DRAW_NLAYERS] == 2
     wind = orc.wind_speed_for((100, 10000))
-    assert rec[_lib.DRAW_WX_0] == wind[0] * np.cos(orc.WIND_DIR[0])        # 12 m/s: integer altitudes
-    assert rec[_lib.DRAW_WY_1] == wind[1] * np.sin(orc.WIND_DIR[1])
+    assert rec[_lib.layer_slot(0, _lib.LAYER_WX)] == wind[0] * np.cos(orc.WIND_DIR[0])        # 12 m/s: integer altitudes
+    assert rec[_lib.layer_slot(1, _lib.LAYER_WY)] == wind[1] * np.sin(orc.WIND_DIR[1])
     recf = psfrec.draw_record([0.7, 0.3], (100., 10000.), 1.0, 25.)
-    assert recf[_lib.DRAW_WX_0] == 12.5 * np.cos(orc.WIND_DIR[0])
+    assert recf[_lib.layer_slot(0, _lib.LAYER_WX)] == 12.5 * np.cos(orc.WIND_DIR[0])
     cn2 = np.array([0.7, 0.3])
     cn2 /= cn2.sum()
-    assert rec[_lib.DRAW_CPHI_1] == 0.0229 * (cn2[1] ** (-3 / 5) * r0) ** (-5 / 3)
+    assert rec[_lib.layer_slot(1, _lib.LAYER_CPHI)] == 0.0229 * (cn2[1] ** (-3 / 5) * r0) ** (-5 / 3)
     with pytest.raises(ValueError):
         psfrec.draw_record([0.5, 0.3, 0.2], (100, 5000, 10000), 1.0, 25.)   # reference: ValueError too
+    # extension: explicit wind directions lift the limit, the zenith angle enters r0
+    rec3 = psfrec.draw_record([0.5, 0.3, 0.2], (100., 5000., 10000.), 1.0, 25., zenith=30., wind_dir=[0.1, 0.2, 0.3])
+    assert rec3[_lib.DRAW_NLAYERS] == 3 and rec3[_lib.DRAW_R0] == orc.seeing2r01(1.0, 0.5, 30.)
+    assert rec3[_lib.layer_slot(2, _lib.LAYER_WY)] == 12.5 * np.sin(0.3)
+    with pytest.raises(ValueError):
+        psfrec.draw_record(np.ones(9), np.arange(9.), 1.0, 25., wind_dir=np.zeros(9))
 
 
 def test_vectorised_records_agree_with_scalar():
