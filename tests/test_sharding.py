@@ -12,14 +12,14 @@ from muse_psfr_b200 import sharding
 
 
 def fake_compute(lam, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs_mode=False):
-    """Deterministic stand-in for the CUDA call: values depend only on the draw's inputs."""
+    """Deterministic stand-in for the CUDA call: values depend only on the (draw, wavelength) inputs."""
     nd, nl = seeing.size, lam.size
     fit = np.zeros((nd, nl, 16))
     fit[:, :, 5] = seeing[:, None] * 4 + lam[None, :] * 1e-3
     fit[:, :, 4] = GL[:, None] + L0[:, None] * 0.01
     h = np.array(h, dtype=float)
     fit[:, :, 0] = (h[:, 0] if h.ndim == 2 else h[0])[..., None] if h.ndim == 2 else h[0]
-    cube = np.ones((nd, nl, 40, 40)) * seeing[:, None, None, None]
+    cube = np.ones((nd, nl, 40, 40)) * seeing[:, None, None, None] * lam[None, :, None, None]
     return fit, cube
 
 
@@ -31,6 +31,20 @@ def test_partition_covers_everything():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_grid_splits_wavelengths_when_draws_run_out():
+    """draws first; one draw on 8 ranks splits the 35 wavelengths (configs 1, 3, 5)."""
+    assert sharding.grid_of(4096, 35, 8) == (8, 1)
+    assert sharding.grid_of(1, 35, 8) == (1, 8)
+    assert sharding.grid_of(3, 35, 8) == (3, 2)
+    assert sharding.grid_of(1, 3, 8) == (1, 3)
+    for ndraw, nlam, world in ((1, 35, 8), (3, 35, 8), (30, 35, 4), (1, 3, 8), (5, 1, 2)):
+        seen = np.zeros((ndraw, nlam), dtype=int)
+        for r in range(world):
+            (d0, d1), (l0, l1) = sharding.block_of(ndraw, nlam, world, r)
+            seen[d0:d1, l0:l1] += 1
+        assert (seen == 1).all()
 
 
 def _inputs(n):
@@ -52,7 +66,7 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n', [5, 8])
+@pytest.mark.parametrize('n', [1, 5, 8])   # n = 1: the wavelength axis is split instead
 def test_two_rank_gather_matches_serial(tmp_path, n):
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
