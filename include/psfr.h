@@ -187,6 +187,11 @@ enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3,
 PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
 
 /* Introspection used by tests and the bench --------------------------------------- */
+/* numeric properties of a context: option values, capacities, and the number of sampled row-pass
+ * frequencies kept per PSF in the hand-off buffer between the two passes of the pruned stage B */
+enum { PSFR_INFO_Y_COLS = 1, PSFR_INFO_EXP_CUT = 2, PSFR_INFO_EXP_GRADE = 3, PSFR_INFO_F32_ROWS = 4,
+       PSFR_INFO_ROW_KERNEL = 5, PSFR_INFO_MAX_PLANES = 6, PSFR_INFO_MAX_LAMBDA = 7, PSFR_INFO_DIM = 8 };
+PSFR_API int psfr_get_info(const psfr_ctx* ctx, int key, double* out);
 PSFR_API int psfr_get_otf(psfr_ctx* ctx, double* out);            /* [dim/2+2][dim] half-plane telescope OTF */
 PSFR_API int psfr_get_structure_function(psfr_ctx* ctx, int plane, double* out); /* [dim/2+2][dim], transposed half-plane */
 /* test hook: y[i] = the device exp() used for exp(-Dphi/2) (csrc/fast_exp.cuh), x[i] <= 0 */

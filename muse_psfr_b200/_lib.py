@@ -33,6 +33,8 @@ OPT_EXP_CUT = 1
 OPT_EXP_GRADE = 2
 OPT_F32_ROWS = 3
 OPT_ROW_KERNEL = 4
+INFO_KEYS = {'y_cols': 1, 'exp_cut': 2, 'exp_grade': 3, 'f32_rows': 4, 'row_kernel': 5, 'max_planes': 6,
+             'max_lambda': 7, 'dim': 8}
 
 
 class PsfrError(RuntimeError):
@@ -69,6 +71,7 @@ _SIGNATURES = {
     'psfr_get_structure_function': (_I, [_P, _I, _P]),
     'psfr_debug_exp': (_I, [_P, _I, _P, _P]),
     'psfr_kernel_launches': (ctypes.c_longlong, [_P]),
+    'psfr_get_info': (_I, [_P, _I, ctypes.POINTER(_D)]),
     'psfr_last_hot_timing': (_I, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I), ctypes.POINTER(ctypes.c_longlong)]),
 }
 
@@ -303,6 +306,15 @@ class Context:
         y = np.empty_like(x)
         self._check(self._lib.psfr_debug_exp(self._handle(), x.size, ptr(x), ptr(y)))
         return y
+
+    def info(self):
+        """Numeric properties of the native context (psfr_get_info) as a dict."""
+        out = {}
+        for name, key in INFO_KEYS.items():
+            v = _D()
+            self._check(self._lib.psfr_get_info(self._handle(), key, ctypes.byref(v)))
+            out[name] = v.value
+        return out
 
     def kernel_launches(self):
         return int(self._lib.psfr_kernel_launches(self._handle()))

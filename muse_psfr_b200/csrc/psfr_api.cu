@@ -54,6 +54,9 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
 static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStream_t s) {
     if (nlam < 1 || nlam > c->max_lambda)
         return set_error(c, PSFR_E_CAPACITY, "nlam=%d outside [1, %d]", nlam, c->max_lambda);
+    if ((int)c->lam_tables.size() == nlam && std::equal(lam_host, lam_host + nlam, c->lam_tables.begin()))
+        return PSFR_OK;   // the tables of these wavelengths are already on the device
+    c->lam_tables.clear();
     const int kN = c->N;
     std::vector<double> cl(nlam), fr((size_t)nlam * kPSF);
     std::vector<uint16_t> kx((size_t)nlam * kNS);
@@ -104,6 +107,7 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     }
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kaddr, ka.data(), ka.size() * sizeof(ushort2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));   // the host vectors go out of scope
+    c->lam_tables.assign(lam_host, lam_host + nlam);
     return PSFR_OK;
 }
 
@@ -665,6 +669,21 @@ int psfr_set_option(psfr_ctx* c, int key, double value) {
 }
 
 long long psfr_kernel_launches(const psfr_ctx* c) { return c ? c->launches : 0; }
+
+int psfr_get_info(const psfr_ctx* c, int key, double* out) {
+    if (!c || !out) return PSFR_E_ARG;
+    switch (key) {
+        case PSFR_INFO_Y_COLS: *out = kNS; return PSFR_OK;
+        case PSFR_INFO_EXP_CUT: *out = c->exp_cut; return PSFR_OK;
+        case PSFR_INFO_EXP_GRADE: *out = c->exp_grade; return PSFR_OK;
+        case PSFR_INFO_F32_ROWS: *out = c->f32_rows; return PSFR_OK;
+        case PSFR_INFO_ROW_KERNEL: *out = c->row_kernel; return PSFR_OK;
+        case PSFR_INFO_MAX_PLANES: *out = c->max_planes; return PSFR_OK;
+        case PSFR_INFO_MAX_LAMBDA: *out = c->max_lambda; return PSFR_OK;
+        case PSFR_INFO_DIM: *out = c->N; return PSFR_OK;
+        default: return PSFR_E_ARG;
+    }
+}
 
 int psfr_last_hot_timing(psfr_ctx* c, double* ms, int* launches, long long* psfs) {
     if (!c) return set_error(c, PSFR_E_ARG, "NULL context");

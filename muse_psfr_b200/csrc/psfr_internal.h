@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <vector>
 #include "../../include/psfr.h"
 
 namespace psfr {
@@ -110,6 +111,10 @@ struct Ctx {
     const void* smem_funcs[64] = {nullptr};
     size_t smem_bytes[64] = {0};
     int n_smem_funcs = 0;
+
+    // wavelengths whose tables (set_lambda_tables) / MUSE kernels (run_build_kernels) currently sit on the
+    // device: a call with the same wavelengths skips the rebuild and its host synchronisation
+    std::vector<double> lam_tables, lam_kernels;
 
     char err[512] = {0};
 };

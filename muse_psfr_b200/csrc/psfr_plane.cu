@@ -5,6 +5,7 @@
 //   fit_kernel      : 5-parameter circular Moffat least squares by Levenberg-Marquardt with
 //                     analytic Jacobian (fit_psf_cube -> mpdaf moffat_fit, :861-871)
 //   mean / polyfit  : time mean of cubes (:1104) and polynomial smoothing (:1174-1210)
+#include <algorithm>
 #include "psfr_internal.h"
 #include "fast_exp.cuh"
 
@@ -511,7 +512,11 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
         int rc = run_kernel_spectra(c, ndraw, c->d_kern_tt, c->d_khat_tt, s);
         if (rc) return rc;
     }
+    if (mu && (int)c->lam_kernels.size() == nlam &&
+        std::equal(lambda_nm_host, lambda_nm_host + nlam, c->lam_kernels.begin()))
+        mu = false;   // the MUSE kernels of these wavelengths and their spectra are already on the device
     if (mu) {
+        c->lam_kernels.clear();
         // muse_intrinsic_psf (psfrec.py:1160-1168, np.polyval = Horner) and alpha = fwhm/0.2/(2 sqrt(2^(1/beta)-1)) (:923-924)
         static const double pol_beta[6] = {-0.83704697, 1.1337153, 0.0609222, -1.35581762, 1.15237178, 2.2106042};
         static const double pol_fwhm[6] = {0.60467385, -1.58905792, 1.75293264, -1.0368302, 0.21487023, 0.34851139};
@@ -534,6 +539,7 @@ int run_build_kernels(Ctx* c, int ndraw, int nlam, const double* lambda_nm_host,
         PSFR_LAUNCH_CHECK(c);
         int rc = run_kernel_spectra(c, nlam, c->d_kern_mu, c->d_khat_mu, s);
         if (rc) return rc;
+        c->lam_kernels.assign(lambda_nm_host, lambda_nm_host + nlam);
     }
     return PSFR_OK;
 }

@@ -37,6 +37,8 @@ def test_header_and_binding_agree():
     for name in ('PEAK', 'Y0', 'X0', 'ALPHA', 'N', 'FWHM', 'CHISQ', 'ITER', 'ERR_FWHM', 'FLUX', 'ERR_FLUX', 'NPAR'):
         m = re.search(r'PSFR_FIT_%s = (\d+)' % name, hdr)
         assert int(m.group(1)) == getattr(_lib, 'FIT_' + name)
+    for name, key in _lib.INFO_KEYS.items():
+        assert int(re.search(r'PSFR_INFO_%s = (\d+)' % name.upper(), hdr).group(1)) == key
     # option keys of psfr_set_option
     for name in ('EXP_CUT', 'EXP_GRADE', 'F32_ROWS', 'ROW_KERNEL'):
         m = re.search(r'PSFR_OPT_%s = (\d+)' % name, hdr)
