@@ -468,6 +468,28 @@ def test_batch_config4_sample(psfrec, golden):
     assert np.all(fit[:, :, _lib.FIT_ITER] > 0)
 
 
+def test_parity_sweep_slice(psfrec):
+    """A 16-draw slice of tools/parity_sweep.py (VERDICT r1 task 1): 12 draws of the config-4 stream + 4
+    of the sweep's corners x all 35 wavelengths, default (cut + graded) and all-FP64 options, against the
+    oracle run on all host cores.  The full sweep's figures are committed under profiles/."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import parity_sweep as ps
+    seeing, GL, L0, h = ps.config4_draws(12, corners=True)
+    keep = np.r_[0:12, [12, 15, 16, 19]]          # (0.4, 9, 0.3), (0.4, 29, 0.95), (2.0, 9, 0.3), (2.0, 29, 0.95)
+    seeing, GL, L0, h = seeing[keep], GL[keep], L0[keep], h[keep]
+    ref = ps.oracle_many([(LBDA35, seeing[i], GL[i], L0[i], h[i], {}) for i in range(16)])
+    ref_cube = np.stack([r[0] for r in ref])
+    ref_fw, ref_n = np.stack([r[1] for r in ref]), np.stack([r[2] for r in ref])
+    for name, opts in ps.OPTION_SETS.items():
+        fit, cube = ps.gpu_batch(psfrec, opts, LBDA35, seeing, GL, L0, h=h)
+        res = ps.compare(cube, fit, ref_cube, ref_fw, ref_n)
+        assert res['finite'] and res['not_converged'] == 0, (name, res)
+        assert res['img_rel'] < PSF_RTOL and res['img_peak'] < PSF_RTOL, (name, res)
+        assert res['fwhm_rel'] < FIT_RTOL and res['beta_rel'] < FIT_RTOL, (name, res)
+
+
 def test_batch_is_independent_of_chunking(psfrec):
     """Size-independent property at batch scale: a draw's result does not depend on which
     other draws share its launch (chunk of 64 planes vs chunks of 7)."""
