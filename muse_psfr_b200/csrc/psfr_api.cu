@@ -99,13 +99,51 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_lam, cl.data(), nlam * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_frac, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kidx, kx.data(), kx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-    // where the row kernel finds X[k] and X[-k] in its natural-order dump (per 1280-point sub-transform)
-    std::vector<ushort2> ka(kx.size());
-    for (size_t i = 0; i < kx.size(); ++i) {
-        const int k = kx[i], km = (kN - k) % kN;
-        ka[i] = make_ushort2((unsigned short)nat_addr(k % kNB), (unsigned short)nat_addr(km % kNB));
+    // Row-pass frequencies kept between the passes: the samples of the first 20 output pixels (k <= 0);
+    // sample 1 (k = -npix/2 + 1) has weight exactly 0 (frac[0] = 0) and gives its slot to k = 0, the live
+    // sample of pixel 20.  xmap: which sample index holds +k / -k of each kept frequency.
+    std::vector<uint16_t> kc((size_t)nlam * kNC);
+    std::vector<short2> xm((size_t)nlam * kNC);
+    std::vector<ushort2> ka((size_t)nlam * kNC);
+    std::vector<double2> wc(c->NF == 2 ? (size_t)nlam * 2 * kNC : 0);
+    for (int l = 0; l < nlam; ++l) {
+        const uint16_t* kxl = kx.data() + (size_t)l * kNS;
+        bool live[kNS], covered[kNS];
+        for (int y = 0; y < kPSF; ++y) {
+            live[2 * y] = true;
+            live[2 * y + 1] = fr[(size_t)l * kPSF + y] != 0.0;
+        }
+        for (int x = 0; x < kNS; ++x) covered[x] = false;
+        for (int j = 0; j < kNC; ++j) {
+            const int k = (j == 1) ? 0 : kxl[j], km = (kN - k) % kN;
+            kc[(size_t)l * kNC + j] = (uint16_t)k;
+            int xd = -1, xf = -1;
+            for (int x = 0; x < kNS; ++x) {
+                if (!live[x]) continue;
+                if (kxl[x] == k && xd < 0) xd = x;
+                if (kxl[x] == km && xf < 0) xf = x;
+            }
+            if (xf == xd) xf = -1;
+            if (xd >= 0) covered[xd] = true;
+            if (xf >= 0) covered[xf] = true;
+            xm[(size_t)l * kNC + j] = make_short2((short)xd, (short)xf);
+            // where the row kernel finds X[k] and X[-k] in its natural-order dump (per 1280-point sub-transform)
+            ka[(size_t)l * kNC + j] = make_ushort2((unsigned short)nat_addr(k % kNB), (unsigned short)nat_addr(km % kNB));
+            if (c->NF == 2) {
+                wc[((size_t)l * 2) * kNC + j] = unit_root(k, kN);
+                wc[((size_t)l * 2 + 1) * kNC + j] = unit_root(km, kN);
+            }
+        }
+        for (int x = 0; x < kNS; ++x)
+            if (live[x] && !covered[x])
+                return set_error(c, PSFR_E_UNSUPPORTED, "wavelength %g nm: sample %d (k = %d) has no mirror among the kept "
+                                 "frequencies", lam_host[l], x, (int)kxl[x]);
     }
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_kcol, kc.data(), kc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    PSFR_CUDA(c, cudaMemcpyAsync(c->d_xmap, xm.data(), xm.size() * sizeof(short2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kaddr, ka.data(), ka.size() * sizeof(ushort2), cudaMemcpyHostToDevice, s));
+    if (c->NF == 2)
+        PSFR_CUDA(c, cudaMemcpyAsync(c->d_wcol, wc.data(), wc.size() * sizeof(double2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaStreamSynchronize(s));   // the host vectors go out of scope
     c->lam_tables.assign(lam_host, lam_host + nlam);
     return PSFR_OK;
@@ -185,7 +223,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_draws); cudaFree(c->d_misc); cudaFree(c->d_lam); cudaFree(c->d_kidx); cudaFree(c->d_frac);
     cudaFree(c->d_kern_tt); cudaFree(c->d_kern_mu); cudaFree(c->d_cube); cudaFree(c->d_cube2);
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
-    cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
+    cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_wcol); cudaFree(c->d_kcol); cudaFree(c->d_xmap); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
     cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -260,6 +298,9 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_tw, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
     CK(dev_alloc(c, &c->d_twc, (size_t)kNB));
     CK(dev_alloc(c, &c->d_wsamp, LM * 2 * kNS));
+    CK(dev_alloc(c, &c->d_wcol, LM * 2 * kNC));
+    CK(dev_alloc(c, &c->d_kcol, LM * kNC));
+    CK(dev_alloc(c, &c->d_xmap, LM * kNC));
     CK(dev_alloc(c, &c->d_pup, (size_t)kNH * kNH));
     CK(dev_alloc(c, &c->d_otf, (size_t)kRows * kN));
     CK(dev_alloc(c, &c->d_geom, (size_t)3 * kAO * kAO));
@@ -274,8 +315,10 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         CK(dev_alloc(c, &c->d_tw32, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
     }
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
-    CK(dev_alloc(c, &c->d_ybuf, P * LM * kNS * kRows));
+    CK(dev_alloc(c, &c->d_ybuf, P * LM * kNC * kRows));
     CK(dev_alloc(c, &c->d_samp, P * LM * kNS * kNS));
+    // samples with bilinear weight 0 are never written: keep them finite (0 * stale value must be 0)
+    CKC(cudaMemset(c->d_samp, 0, P * LM * kNS * kNS * sizeof(double)));
     CK(dev_alloc(c, &c->d_ao, P * kAO * kAO));
     CK(dev_alloc(c, &c->d_draws, P * PSFR_DRAW_NPAR));
     CK(dev_alloc(c, &c->d_misc, (size_t)misc_size(max_planes)));
@@ -283,7 +326,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     CK(dev_alloc(c, &c->d_csort, LM));
     CK(dev_alloc(c, &c->d_lorder, LM));
     CK(dev_alloc(c, &c->d_kidx, LM * kNS));
-    CK(dev_alloc(c, &c->d_kaddr, LM * kNS));
+    CK(dev_alloc(c, &c->d_kaddr, LM * kNC));
     CK(dev_alloc(c, &c->d_frac, LM * kPSF));
     CK(dev_alloc(c, &c->d_kern_tt, P * kKW * kKW));
     CK(dev_alloc(c, &c->d_kern_mu, LM * kKW * kKW));
@@ -673,7 +716,7 @@ long long psfr_kernel_launches(const psfr_ctx* c) { return c ? c->launches : 0; 
 int psfr_get_info(const psfr_ctx* c, int key, double* out) {
     if (!c || !out) return PSFR_E_ARG;
     switch (key) {
-        case PSFR_INFO_Y_COLS: *out = kNS; return PSFR_OK;
+        case PSFR_INFO_Y_COLS: *out = kNC; return PSFR_OK;
         case PSFR_INFO_EXP_CUT: *out = c->exp_cut; return PSFR_OK;
         case PSFR_INFO_EXP_GRADE: *out = c->exp_grade; return PSFR_OK;
         case PSFR_INFO_F32_ROWS: *out = c->f32_rows; return PSFR_OK;

@@ -54,9 +54,9 @@ int hot_event(Ctx* c, int which, cudaStream_t s);   // psfr_api.cu: CUDA-event b
 struct HotParams {
     const double* D;       // [nplanes][kRows][N]
     const double* T;       // [kRows][N]
-    double2* Y;            // [nplanes][nlam][kNS][kRows]
-    const ushort2* kaddr;  // [nlam][kNS] where X[k], X[-k] of the sampled frequencies sit in the natural-order dump
-    const double2* wsamp;  // [nlam][2][kNS] NF = 2: w_N^k of the sampled outputs and of their mirrors
+    double2* Y;            // [nplanes][nlam][kNC][kRows]
+    const ushort2* kaddr;  // [nlam][kNC] where X[k], X[-k] of the kept frequencies sit in the natural-order dump
+    const double2* wsamp;  // [nlam][2][kNC] NF = 2: w_N^k of the kept frequencies and of their mirrors
     const double* dmin;    // [nplanes][kRows] smallest D of each row (StoreDphi)
     const float* D32;      // single-precision copies of D and T (dim 1280)
     const float* T32;
@@ -78,6 +78,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
     constexpr int kStages = C::Stages, kHotWarps = C::Warps, kTile = C::Tile, kN = D::N, kRows = D::Rows,
                   kPairs = D::Pairs;
     constexpr uint32_t kTileBytes = C::TileBytes, kTileBytes32 = C::TileBytes32;
+    constexpr int kQ = (kNC + 31) / 32;   // kept frequencies per lane
     constexpr size_t kStageDoubles = C::StageBytes / sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -204,11 +205,11 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 if (item >= 0) {
                     const int plane = item / kPairs, rp = item % kPairs, la = la_of[s];
                     for (int i = warp; i < la; i += kHotWarps) {
-                        double2* out = p.Y + ((size_t)plane * p.nlam + (tabbed ? tab_lo[i] : __ldg(p.lorder + i))) * kNS * kRows + 2 * rp;
+                        double2* out = p.Y + ((size_t)plane * p.nlam + (tabbed ? tab_lo[i] : __ldg(p.lorder + i))) * kNC * kRows + 2 * rp;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
+                        for (int k = 0; k < kQ; ++k) {
                             const int y = lane + 32 * k;
-                            if (y < kNS) {
+                            if (y < kNC) {
                                 st_global_256(out + (size_t)y * kRows, make_double2(0.0, 0.0), make_double2(0.0, 0.0));
                             }
                         }
@@ -261,10 +262,10 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
             const float* sT32 = sD32 + kTile;
             const int plane = item / kPairs, rp = item % kPairs;
             auto lam_of = [&](int pos) { return tabbed ? tab_lo[pos] : __ldg(p.lorder + pos); };
-            auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp; };
+            auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNC * kRows + 2 * rp; };
             // untangle the two packed real rows: row 2rp from the even, row 2rp+1 from the odd part
             auto store_rows = [&](double2* out, int i, double2 za, double2 zb) {
-                if (lane + 32 * i < kNS)
+                if (lane + 32 * i < kNC)
                     st_global_256(out + (size_t)(lane + 32 * i) * kRows,
                                   make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
                                   make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
@@ -284,12 +285,12 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 const float nB = (float)(-cB * 1.44269504088896338700);
                 // c_B <= c_A: an entry below the cut at B is below it at A
                 const int cut32 = __float_as_int((float)(p.cut * (tabbed ? tab_rc[posB] : 1.0 / cB)));
-                ushort2 kaA[3], kaB[3];   // dump addresses of X[k], X[-k] for this lane's sampled frequencies
+                ushort2 kaA[kQ], kaB[kQ];   // dump addresses of X[k], X[-k] for this lane's sampled frequencies
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const bool in = lane + 32 * i < kNS;
-                    kaA[i] = in ? __ldg(p.kaddr + (size_t)lamA * kNS + lane + 32 * i) : make_ushort2(0, 0);
-                    kaB[i] = in ? __ldg(p.kaddr + (size_t)lamB * kNS + lane + 32 * i) : make_ushort2(0, 0);
+                for (int i = 0; i < kQ; ++i) {
+                    const bool in = lane + 32 * i < kNC;
+                    kaA[i] = in ? __ldg(p.kaddr + (size_t)lamA * kNC + lane + 32 * i) : make_ushort2(0, 0);
+                    kaB[i] = in ? __ldg(p.kaddr + (size_t)lamB * kNC + lane + 32 * i) : make_ushort2(0, 0);
                 }
                 Z2 vf[40];
 #pragma unroll
@@ -325,13 +326,13 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 float2* xf = reinterpret_cast<float2*>(xb);
                 // natural-order dump of one component (both wavelengths) per round; wavelength A reads
                 // the first halves at its own sampled frequencies, B the second halves at its own
-                float2 fa[3], fb[3], ga[3], gb[3];   // A: X[kA], X[-kA]; B likewise
+                float2 fa[kQ], fb[kQ], ga[kQ], gb[kQ];   // A: X[kA], X[-kA]; B likewise
 #pragma unroll
                 for (int cpt = 0; cpt < 2; ++cpt) {
                     fft_dump<kR3>(vf, xf, lane, cpt);
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
+                    for (int i = 0; i < kQ; ++i) {
                         const float a = xf[kaA[i].x].x, am = xf[kaA[i].y].x;
                         const float b = xf[kaB[i].x].y, bm = xf[kaB[i].y].y;
                         if (cpt == 0) {
@@ -345,7 +346,7 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 double2* outA = out_of(lamA);
                 double2* outB = out_of(lamB);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
+                for (int i = 0; i < kQ; ++i) {
                     store_rows(outA, i, make_double2((double)fa[i].x, (double)fa[i].y),
                                make_double2((double)fb[i].x, (double)fb[i].y));
                     if (two)
@@ -359,11 +360,11 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                 double2* out = out_of(lam);
                 const double negc = -cl;
                 // where the sampled frequencies kA and their mirrors kB = -kA sit in the natural-order dump
-                const ushort2* kx = p.kaddr + (size_t)lam * kNS;
-                ushort2 ka[3];
+                const ushort2* kx = p.kaddr + (size_t)lam * kNC;
+                ushort2 ka[kQ];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) ka[i] = (lane + 32 * i < kNS) ? __ldg(kx + lane + 32 * i) : make_ushort2(0, 0);
-                double2 za[3], zb[3];   // X[kA], X[kB] accumulated over the NF interleaved sub-sequences
+                for (int i = 0; i < kQ; ++i) ka[i] = (lane + 32 * i < kNC) ? __ldg(kx + lane + 32 * i) : make_ushort2(0, 0);
+                double2 za[kQ], zb[kQ];   // X[kA], X[kB] accumulated over the NF interleaved sub-sequences
                 // Cut and grade thresholds on D itself, tested on the integer pipe: a non-negative
                 // float (double) orders like its bit pattern (high word); the SIGNED compare keeps a
                 // D rounded slightly below zero alive.
@@ -443,13 +444,13 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         }
                     }
                     warp_fft<kR3>(v, xb, tw1, tw2, lane);
-                    double2 fa[3], fb[3];
+                    double2 fa[kQ], fb[kQ];
 #pragma unroll
                     for (int cpt = 0; cpt < 2; ++cpt) {
                         fft_dump<kR3>(v, xb, lane, cpt);
                         __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
+                        for (int i = 0; i < kQ; ++i) {
                             comp_set(fa[i], cpt, xb[ka[i].x]);
                             comp_set(fb[i], cpt, xb[ka[i].y]);
                         }
@@ -457,16 +458,16 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                     }
                     if (NF == 1) {
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
+                        for (int i = 0; i < kQ; ++i) {
                             za[i] = fa[i];
                             zb[i] = fb[i];
                         }
                     } else if (sub == 0) {
                         // park F0 in the output slots (L2-resident) instead of 12 more live registers
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
+                        for (int i = 0; i < kQ; ++i) {
                             const int y = lane + 32 * i;
-                            if (y < kNS) {
+                            if (y < kNC) {
                                 double2* o = out + (size_t)y * kRows;
                                 o[0] = fa[i];
                                 o[1] = fb[i];
@@ -474,20 +475,20 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
                         }
                     } else {
                         // X[k] = F0[k mod 1280] + w_N^k F1[k mod 1280]
-                        const double2* ws = p.wsamp + (size_t)lam * 2 * kNS;
+                        const double2* ws = p.wsamp + (size_t)lam * 2 * kNC;
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
+                        for (int i = 0; i < kQ; ++i) {
                             const int y = lane + 32 * i;
-                            if (y < kNS) {
+                            if (y < kNC) {
                                 const double2* o = out + (size_t)y * kRows;
                                 za[i] = cadd(o[0], cmul(fa[i], __ldg(ws + y)));
-                                zb[i] = cadd(o[1], cmul(fb[i], __ldg(ws + kNS + y)));
+                                zb[i] = cadd(o[1], cmul(fb[i], __ldg(ws + kNC + y)));
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 3; ++i) store_rows(out, i, za[i], zb[i]);
+                for (int i = 0; i < kQ; ++i) store_rows(out, i, za[i], zb[i]);
             }
         }
         // move on to the next round's first unit BEFORE its barrier: the items that lie wholly
@@ -499,10 +500,14 @@ hot_rows_kernel(HotParams p, const double2* __restrict__ g_tw) {
 }
 
 // ---------------- pruned column pass
-// line f = ((draw*nlam + lam)*40 + m): sampled rows 2m, 2m+1 of that PSF (adjacent in Y, one
-// contiguous 2*Rows*16-byte block), summed over the ndir planes of the draw, Hermitian-extended
-// along the half-plane row index, transformed, and only the 80 sampled outputs kept:
-//   S[img][2m + c][j] = scale * (-1)^(k_{2m+c} + k_j) * {Re, Im}(X[k_j]).
+// line f = ((draw*nlam + lam)*20 + m): kept row-pass frequencies 2m, 2m+1 of that PSF (adjacent in Y,
+// one contiguous 2*Rows*16-byte block), summed over the ndir planes of the draw, Hermitian-extended
+// along the half-plane row index and transformed as the real and imaginary part of one complex
+// line.  Only the 80 sampled outputs k_j AND their mirrors -k_j are kept: with P the (real,
+// point-symmetric) PSF and kc the line's row-pass frequency,
+//   S[img][x][j] = scale * (-1)^(kc + k_j) * P[k_j][kc]    for the sample x whose frequency is +kc,
+//   S[img][x'][j] = scale * (-1)^(kc + k_j) * P[-k_j][kc]  for the sample x' whose frequency is -kc
+// (P[k_j][-kc] = P[-k_j][kc]): 20 transforms per PSF give all 80 x 80 samples (xmap of set_lambda_tables).
 // Every warp owns a private tile that a TMA bulk copy fills while the warp transforms the
 // previous line (the tile is dead as soon as its values sit in registers), so the kernel
 // streams Y at HBM speed instead of waiting on 80 dependent 16-byte loads per lane.
@@ -526,9 +531,11 @@ struct ColCfg {
 };
 
 struct ColParams {
-    const double2* Y;      // [nplanes][nlam][kNS][Rows]
+    const double2* Y;      // [nplanes][nlam][kNC][Rows]
     double* S;             // [nimg][kNS][kNS]
-    const uint16_t* kidx;  // [nlam][kNS]
+    const uint16_t* kidx;  // [nlam][kNS] sampled frequencies
+    const uint16_t* kcol;  // [nlam][kNC] kept row-pass frequencies
+    const short2* xmap;    // [nlam][kNC] sample index of +kcol / -kcol (-1: none)
     const double2* wsamp;  // [nlam][2][kNS] (NF = 2)
     int nlines, nlam, ndir;
     double scale;
@@ -539,6 +546,7 @@ __global__ void __launch_bounds__(ColCfg<NF>::Warps * 32, 1)
 hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
     using D = Dim<NF>;
     using C = ColCfg<NF>;
+    constexpr int kLines = kNC / 2;   // lines (pairs of kept frequencies) per PSF
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);              // one mbarrier per warp
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
@@ -559,9 +567,9 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
     const int gw = blockIdx.x * C::Warps + warp, nw = gridDim.x * C::Warps;
     // tile of (line f, direction d)
     auto src_of = [&](int f, int d) {
-        const int m = f % (kNS / 2), img = f / (kNS / 2);
+        const int m = f % kLines, img = f / kLines;
         const int lam = img % p.nlam, draw = img / p.nlam;
-        return p.Y + (((size_t)(draw * p.ndir + d) * p.nlam + lam) * kNS + 2 * m) * D::Rows;
+        return p.Y + (((size_t)(draw * p.ndir + d) * p.nlam + lam) * kNC + 2 * m) * D::Rows;
     };
     auto fetch = [&](int f, int d) {
         if (lane == 0) {
@@ -574,12 +582,12 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
     uint32_t phase = 0;
 #pragma unroll 1
     for (int f = gw; f < p.nlines; f += nw) {
-        const int m = f % (kNS / 2), img = f / (kNS / 2), lam = img % p.nlam;
+        const int m = f % kLines, img = f / kLines, lam = img % p.nlam;
         const uint16_t* kx = p.kidx + (size_t)lam * kNS;
         int kj[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) kj[i] = (lane + 32 * i < kNS) ? (int)__ldg(kx + lane + 32 * i) : 0;
-        double2 z[3];
+        double2 z[3], zm[3];   // X[k_j], X[-k_j]
 #pragma unroll 1
         for (int sub = 0; sub < NF; ++sub) {
             double2 v[40];
@@ -613,34 +621,50 @@ hot_cols_kernel(ColParams p, const double2* __restrict__ g_tw) {
                 else if (!C::SharedTile && f + nw < p.nlines) fetch(f + nw, 0);
             }
             warp_fft<kR3>(v, xb, tw1, tw2, lane);
-            double2 fz[3];
+            double2 fz[3], fm[3];
 #pragma unroll
             for (int cpt = 0; cpt < 2; ++cpt) {
                 fft_dump<kR3>(v, xb, lane, cpt);
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 3; ++i) comp_set(fz[i], cpt, xb[nat_addr(kj[i] % kNB)]);
+                for (int i = 0; i < 3; ++i) {
+                    comp_set(fz[i], cpt, xb[nat_addr(kj[i] % kNB)]);
+                    comp_set(fm[i], cpt, xb[nat_addr((D::N - kj[i]) % kNB)]);
+                }
                 __syncwarp();
             }
             if (NF == 1 || sub == 0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) z[i] = fz[i];
+                for (int i = 0; i < 3; ++i) {
+                    z[i] = fz[i];
+                    zm[i] = fm[i];
+                }
             } else {
                 const double2* ws = p.wsamp + (size_t)lam * 2 * kNS;
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
-                    if (lane + 32 * i < kNS) z[i] = cadd(z[i], cmul(fz[i], __ldg(ws + lane + 32 * i)));
+                    if (lane + 32 * i < kNS) {
+                        z[i] = cadd(z[i], cmul(fz[i], __ldg(ws + lane + 32 * i)));
+                        zm[i] = cadd(zm[i], cmul(fm[i], __ldg(ws + kNS + lane + 32 * i)));
+                    }
             }
         }
         if (C::SharedTile && f + nw < p.nlines) fetch(f + nw, 0);   // the gathers above are done (__syncwarp)
-        const int k1 = __ldg(kx + 2 * m), k2 = __ldg(kx + 2 * m + 1);
-        double* o = p.S + ((size_t)img * kNS + 2 * m) * kNS;
+        // real part = kept frequency 2m, imaginary part = 2m + 1; each fills the sample row of +kc from
+        // the outputs at k_j and the sample row of -kc from the outputs at -k_j
+        const int kc1 = __ldg(p.kcol + (size_t)lam * kNC + 2 * m), kc2 = __ldg(p.kcol + (size_t)lam * kNC + 2 * m + 1);
+        const short2 x1 = __ldg(p.xmap + (size_t)lam * kNC + 2 * m), x2 = __ldg(p.xmap + (size_t)lam * kNC + 2 * m + 1);
+        double* o = p.S + (size_t)img * kNS * kNS;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int j = lane + 32 * i;
             if (j < kNS) {
-                o[j] = (((k1 + kj[i]) & 1) ? -p.scale : p.scale) * z[i].x;
-                o[kNS + j] = (((k2 + kj[i]) & 1) ? -p.scale : p.scale) * z[i].y;
+                const double s1 = ((kc1 + kj[i]) & 1) ? -p.scale : p.scale;
+                const double s2 = ((kc2 + kj[i]) & 1) ? -p.scale : p.scale;
+                if (x1.x >= 0) o[x1.x * kNS + j] = s1 * z[i].x;
+                if (x1.y >= 0) o[x1.y * kNS + j] = s1 * zm[i].x;
+                if (x2.x >= 0) o[x2.x * kNS + j] = s2 * z[i].y;
+                if (x2.y >= 0) o[x2.y * kNS + j] = s2 * zm[i].y;
             }
         }
     }
@@ -652,7 +676,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     using C = HotCfg<NF>;
     if (int rc = ensure_dynamic_smem(c, hot_rows_kernel<NF>, C::Smem)) return rc;
     const int nplanes = ndraw * ndir;
-    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_kaddr, c->d_wsamp, c->d_dmin, c->d_dphi32,
+    HotParams p{c->d_dphi, c->d_otf, c->d_ybuf, c->d_kaddr, c->d_wcol, c->d_dmin, c->d_dphi32,
                 c->d_otf32, c->d_tw32, c->d_csort, c->d_lorder, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
@@ -671,7 +695,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     // psd_to_psf divides by the PSF sum (= T centre = 1/N^2, cancelling the 1/N^2 of the
     // inverse transform); psf_muse averages the directions.
     if ((rc = ensure_dynamic_smem(c, hot_cols_kernel<NF>, ColCfg<NF>::Smem))) return rc;
-    ColParams q{c->d_ybuf, c->d_samp, c->d_kidx, c->d_wsamp, ndraw * nlam * (kNS / 2), nlam, ndir, 1.0 / ndir};
+    ColParams q{c->d_ybuf, c->d_samp, c->d_kidx, c->d_kcol, c->d_xmap, c->d_wsamp, ndraw * nlam * (kNC / 2), nlam, ndir, 1.0 / ndir};
     int cgrid = (q.nlines + ColCfg<NF>::Warps - 1) / ColCfg<NF>::Warps;
     if (cgrid > c->sm_count) cgrid = c->sm_count;
     hot_cols_kernel<NF><<<cgrid, ColCfg<NF>::Warps * 32, ColCfg<NF>::Smem, s>>>(q, c->d_tw);

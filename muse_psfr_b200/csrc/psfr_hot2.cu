@@ -47,8 +47,8 @@ struct Rows2Params {
     const double* T;       // [kRows][N]
     const float* D32;
     const float* T32;
-    double2* Y;            // [nplanes][nlam][kNS][kRows]
-    const uint16_t* kidx;  // [nlam][kNS]
+    double2* Y;            // [nplanes][nlam][kNC][kRows]
+    const uint16_t* kcol;  // [nlam][kNC] row-pass frequencies kept per PSF
     const double* dmin;    // [nplanes][kRows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
@@ -146,24 +146,27 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
         }
     }
     group_bar(grp);
-    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y]; a packed pair
-    // does it once per wavelength (each has its own sampled frequencies), reading its half
+    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y] of kept frequency y
+    // (the first three warps; warp 2 runs with its upper half clamped so that the shuffle is warp-wide);
+    // a packed pair does it once per wavelength (each has its own frequencies), reading its half
+    if (b < 96) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint16_t* kx = h ? kidx2 : kidx;
-        double2* o = h ? out2 : out;
-        if (h && o == nullptr) break;   // a single transform, or a pair with only one wavelength
-        const int y = b >> 1;
-        const int k = (int)__ldg(kx + y);
-        const int kk = (b & 1) ? (kN - k) % kN : k;
-        const double2 mine = half_of(buf[kk + (kk >> 3)], h);
-        double2 other;
-        other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-        other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-        if (!(b & 1)) {
-            const double2 za = mine, zb = other;
-            st_global_256(o + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
-                          make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+        for (int h = 0; h < 2; ++h) {
+            const uint16_t* kx = h ? kidx2 : kidx;
+            double2* o = h ? out2 : out;
+            if (h && o == nullptr) break;   // a single transform, or a pair with only one wavelength
+            const int y = min(b >> 1, kNC - 1);
+            const int k = (int)__ldg(kx + y);
+            const int kk = (b & 1) ? (kN - k) % kN : k;
+            const double2 mine = half_of(buf[kk + (kk >> 3)], h);
+            double2 other;
+            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+            other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+            if (!(b & 1) && b < 2 * kNC) {
+                const double2 za = mine, zb = other;
+                st_global_256(o + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                              make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+            }
         }
     }
 }
@@ -270,11 +273,11 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 mbar_wait(full + s, (cur / kStages) & 1);
                 seen = true;
                 const int item = item_of[s];
-                if (item >= 0 && b < kNS) {
+                if (item >= 0 && b < kNC) {
                     const int plane = item / kPairs, rp = item % kPairs, la = la_of[s];
                     for (int i = grp; i < la; i += kGroups) {
                         const int lam = tabbed ? tab_lo[i] : __ldg(p.lorder + i);
-                        st_global_256(p.Y + (((size_t)plane * p.nlam + lam) * kNS + b) * kRows + 2 * rp,
+                        st_global_256(p.Y + (((size_t)plane * p.nlam + lam) * kNC + b) * kRows + 2 * rp,
                                       make_double2(0.0, 0.0), make_double2(0.0, 0.0));
                     }
                 }
@@ -316,7 +319,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         const float* sT32 = sD32 + kTile;
         const int plane = item / kPairs, rp = item % kPairs;
         auto lam_of = [&](int pos) { return tabbed ? tab_lo[pos] : __ldg(p.lorder + pos); };
-        auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNS * kRows + 2 * rp; };
+        auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNC * kRows + 2 * rp; };
         auto n2f_of = [&](int pos) {
             return tabbed ? __int_as_float(tab_n2f[pos]) : (float)(-c_of(pos) * 1.44269504088896338700);
         };
@@ -347,8 +350,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
                 }
             }
-            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.kidx + (size_t)lamA * kNS, out_of(lamA),
-                            p.kidx + (size_t)lamB * kNS, two ? out_of(lamB) : nullptr);
+            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.kcol + (size_t)lamA * kNC, out_of(lamA),
+                            p.kcol + (size_t)lamB * kNC, two ? out_of(lamB) : nullptr);
         } else {
             // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
             const int pos = lb + (slot - npair);
@@ -375,7 +378,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
                 }
             }
-            group_transform(x, buf, twr, b, grp, p.kidx + (size_t)lam * kNS, out_of(lam));
+            group_transform(x, buf, twr, b, grp, p.kcol + (size_t)lam * kNC, out_of(lam));
         }
         base += kGroups;
     }
@@ -386,7 +389,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
 int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
     if (c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "the group row kernel is dim-1280 only");
     if (int rc = ensure_dynamic_smem(c, group_rows_kernel, kSmem2)) return rc;
-    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_kidx, c->d_dmin, c->d_csort,
+    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_kcol, c->d_dmin, c->d_csort,
                   c->d_lorder, c->d_tw32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * kPairs) grid = nplanes * kPairs;

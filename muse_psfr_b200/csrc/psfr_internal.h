@@ -24,6 +24,11 @@ struct Dim {
 constexpr int kAO = PSFR_AO_DIM;        // 80
 constexpr int kPSF = PSFR_PSF_DIM;      // 40
 constexpr int kNS = 2 * kPSF;           // 80 sampled rows / columns per PSF
+// The sampled frequencies with a non-zero bilinear weight are closed under negation (up to the single
+// sample -npix/2), and the PSF is point-symmetric: P[-ky][-kx] = P[ky][kx].  The row pass therefore
+// keeps only the kNC = 40 frequencies k <= 0 (set_lambda_tables) and the column pass fills the
+// mirrored samples from its outputs at -ky.
+constexpr int kNC = kPSF;
 constexpr int kKW = 41;                 // Moffat kernel width
 constexpr int kMaxGS = 4;
 constexpr int kMaxDir = 256;            // field directions per draw
@@ -74,15 +79,18 @@ struct Ctx {
     double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
     double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
     int row_kernel = 2;          // dim 1280: 2 group_rows_kernel (psfr_hot2.cu), 1 hot_rows_kernel (PSFR_OPT_ROW_KERNEL)
-    double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNS][rows] pruned row-pass output
+    double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNC][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
+    double2* d_wcol = nullptr;   // [max_lambda][2][kNC] the same for the kept row-pass frequencies (NF = 2)
+    uint16_t* d_kcol = nullptr;  // [max_lambda][kNC] row-pass frequencies kept in d_ybuf
+    short2* d_xmap = nullptr;    // [max_lambda][kNC] sample index whose frequency is +kcol / -kcol (-1: none)
     double* d_samp = nullptr;    // [max_draws*max_lambda][kNS][kNS] PSF samples
     double* d_ao = nullptr;      // [max_planes][80][80] AO-zone PSD (centred, reference orientation)
     double* d_draws = nullptr;   // [max_planes][PSFR_DRAW_NPAR]
     double* d_misc = nullptr;    // small: dirs, poslgs, lambda tables ...
     double* d_lam = nullptr;     // [max_lambda] c_lambda = 0.5 (2 pi/lambda_nm)^2
     uint16_t* d_kidx = nullptr;  // [max_lambda][kNS] sampled output indices (shifted by N/2)
-    ushort2* d_kaddr = nullptr;  // [max_lambda][kNS] dump addresses nat_addr(k mod 1280), nat_addr(-k mod 1280) of those
+    ushort2* d_kaddr = nullptr;  // [max_lambda][kNC] dump addresses nat_addr(k mod 1280), nat_addr(-k mod 1280) of d_kcol
     double* d_frac = nullptr;    // [max_lambda][kPSF] bilinear fractions
     double* d_kern_tt = nullptr; // [max_planes][41][41] normalised tip-tilt kernels
     double* d_kern_mu = nullptr; // [max_lambda][41][41] normalised MUSE kernels
