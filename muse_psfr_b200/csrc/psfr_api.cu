@@ -50,6 +50,42 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
     return PSFR_OK;
 }
 
+// Pass-3 records of the group row kernel (psfr_hot2.cu) for one wavelength: thread pair (2q, 2q+1) gets
+// a kept frequency k and its mirror.  A thread reads buf[base + 21 n3], n3 = 0..7, i.e. 16-byte slot
+// (slot0 + 5 n3) mod 8 with slot0 = (k mod 8 + (k div 8) mod 20) mod 8: the pairs are dealt greedily so
+// that the eight threads of a quarter-warp have as few equal slot0 as the frequency set allows.
+static void group_p3_table(const uint16_t* kc, GroupP3* out) {
+    auto slot0 = [](int k) { return ((k & 7) + ((k >> 3) % 20)) & 7; };
+    bool used[kNC] = {false};
+    int q = 0;
+    for (int g = 0; g < kNC / 4; ++g) {          // quarter-warps of four pairs
+        int cnt[8] = {0};
+        for (int i = 0; i < 4; ++i, ++q) {
+            int best = -1, best_cost = 1 << 30;
+            for (int j = 0; j < kNC; ++j) {
+                if (used[j]) continue;
+                const int k = kc[j], km = (kNB - k) % kNB;
+                const int a = slot0(k), b = slot0(km);
+                const int cost = cnt[a] + cnt[b] + (a == b && k != km ? 1 : 0);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = j;
+                }
+            }
+            used[best] = true;
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const int k = sgn ? (kNB - kc[best]) % kNB : kc[best];
+                ++cnt[slot0(k)];
+                GroupP3& e = out[2 * q + sgn];
+                e.w = unit_root(k, kNB);
+                e.w32 = make_float2((float)e.w.x, (float)e.w.y);
+                e.base = (uint32_t)((k & 7) * 169 + (k >> 3) % 20);
+                e.col = (uint32_t)best;
+            }
+        }
+    }
+}
+
 // wavelength tables: exponent scale, sampled indices, bilinear fractions (psfrec.py:663-664, 682-683)
 static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStream_t s) {
     if (nlam < 1 || nlam > c->max_lambda)
@@ -139,6 +175,12 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
                 return set_error(c, PSFR_E_UNSUPPORTED, "wavelength %g nm: sample %d (k = %d) has no mirror among the kept "
                                  "frequencies", lam_host[l], x, (int)kxl[x]);
     }
+    std::vector<GroupP3> p3;
+    if (c->d_p3) {
+        p3.resize((size_t)nlam * 2 * kNC);
+        for (int l = 0; l < nlam; ++l) group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC);
+        PSFR_CUDA(c, cudaMemcpyAsync(c->d_p3, p3.data(), p3.size() * sizeof(GroupP3), cudaMemcpyHostToDevice, s));
+    }
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kcol, kc.data(), kc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_xmap, xm.data(), xm.size() * sizeof(short2), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kaddr, ka.data(), ka.size() * sizeof(ushort2), cudaMemcpyHostToDevice, s));
@@ -225,7 +267,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_wcol); cudaFree(c->d_kcol); cudaFree(c->d_xmap); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
-    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
+    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_twg); cudaFree(c->d_twg32); cudaFree(c->d_p3); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -313,6 +355,9 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         CK(dev_alloc(c, &c->d_dphi32, P * kRows * kN));
         CK(dev_alloc(c, &c->d_otf32, (size_t)kRows * kN));
         CK(dev_alloc(c, &c->d_tw32, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
+        CK(dev_alloc(c, &c->d_twg, (size_t)kGroupTw));
+        CK(dev_alloc(c, &c->d_twg32, (size_t)kGroupTw));
+        CK(dev_alloc(c, &c->d_p3, LM * 2 * kNC));
     }
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNC * kRows));
@@ -358,6 +403,18 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         for (size_t i = 0; i < tw1.size(); ++i) tw32[i] = make_float2((float)tw1[i].x, (float)tw1[i].y);
         for (size_t i = 0; i < tw2.size(); ++i) tw32[tw1.size() + i] = make_float2((float)tw2[i].x, (float)tw2[i].y);
         CKC(cudaMemcpy(c->d_tw32, tw32.data(), tw32.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if (c->d_twg) {
+        std::vector<double2> twg(kGroupTw);
+        std::vector<float2> twg32(kGroupTw);
+        for (int n2 = 0; n2 < 20; ++n2)
+            for (int k1 = 1; k1 < 8; ++k1) {
+                const double2 w = unit_root((long long)n2 * k1, 160);
+                twg[n2 * 7 + k1 - 1] = w;
+                twg32[n2 * 7 + k1 - 1] = make_float2((float)w.x, (float)w.y);
+            }
+        CKC(cudaMemcpy(c->d_twg, twg.data(), twg.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_twg32, twg32.data(), twg32.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
     {
         std::vector<double2> twc(kNB);

@@ -5,21 +5,30 @@
 //   hot_rows_kernel : one WARP = one 1280-point transform, 40 points per lane in registers,
 //                     ~70 KB of unrolled code per unit, 8 warps per SM (253 registers);
 //   group_rows_kernel: one GROUP of 160 threads = one transform that lives in shared memory
-//                     (22.5 KB), three radix passes (8, 8, 20) separated by group barriers,
-//                     8 or 20 points per thread, a few KB of code, 15 warps per SM.
+//                     (21.6 KB), two full radix passes (8, 20) and a PRUNED third one that evaluates
+//                     only the 80 outputs the column pass needs (the 40 kept frequencies and their
+//                     mirrors), a few KB of code, 15 warps per SM.
 //
-// Index maps (those of warp_fft.cuh): n = n1*160 + n2*20 + n3,  k = k1 + 8*k2 + 64*k3.
-//   pass 1 : thread b = n2*20 + n3 evaluates its own eight inputs x[n1*160 + b] (both rows:
+// Index maps:  n = n1*160 + n2*8 + n3,  k = k1 + 8*k2 + 160*k3  (n1, n3, k1, k3 < 8; n2, k2 < 20).
+//   pass 1 : thread b = n2*8 + n3 evaluates its own eight inputs x[n1*160 + b] (both rows:
 //            exp(-c D) * T, graded like hot_rows_kernel but per 32-cell segment), radix-8 over
-//            n1, times w_N^(b k1)                       -> buf[k1*172 + n2*21 + n3]
-//   pass 2 : thread (k1, n3) radix-8 over n2, times w_160^(n3 k2), in place
-//   pass 3 : threads (k1, k2) < 64: radix-20 over n3 -> natural order buf[k + (k >> 3)]
-//   gather : thread pairs (2y, 2y+1) read X[k_y], X[-k_y], untangle the two real rows, store.
-// The strides 172 / 21 and the skews make every 16-byte access pattern above conflict-free
-// (quarter-warps hit eight distinct 16-byte slots).
+//            n1, times w_160^(n2 k1)                    -> buf[k1*169 + n3*21 + n2]
+//   pass 2 : threads (k1, n3) < 64: radix-20 over n2 (Good-Thomas 4 x 5, no twiddles), in place
+//                                                        -> buf[k1*169 + n3*21 + k2]
+//   pass 3 : threads 80..159, one per needed output k: X[k] = sum_n3 buf[k1*169 + n3*21 + k2] (w_N^k)^n3
+//            by Horner's rule - the twiddle between passes 2 and 3 and the radix-8 phase are one
+//            power series in w_N^k, held per (wavelength, thread) in a table (set_lambda_tables);
+//            adjacent threads hold X[k], X[-k]: one shuffle, untangle the two real rows, one
+//            32-byte store per kept frequency.
+// The full transform's third pass (64 x radix-20, natural-order dump, gather of 160 values) took two
+// more trips through shared memory and the kernel is shared-memory-bound (profiles/).
+// Strides 169 / 21 make the 16-byte accesses of passes 1 and 2 conflict-free (a quarter-warp hits
+// eight distinct 16-byte slots); in pass 3 the slot of a thread is (k1 + k2 + 5 n3) mod 8 and the host
+// orders the outputs so that the eight threads of a quarter-warp differ in (k1 + k2) mod 8 wherever
+// the wavelength's frequency set allows it.
 //
 // Row pairs below exp(-f32_min) run the same passes in single precision, two wavelengths at a time
-// as the halves of one packed transform (Z2, warp_fft.cuh).
+// as the halves of one packed transform (Z2, warp_fft.cuh); each half has its own pass-3 outputs.
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 #include "tma.cuh"
@@ -32,15 +41,18 @@ namespace {
 
 constexpr int kGroups = 3;                // transforms in flight per CTA
 constexpr int kGT = 160;                  // threads per group
-constexpr int kBuf = 1440;                // double2 per transform buffer (layouts above)
+constexpr int kS2 = 21, kS1 = 8 * kS2 + 1;   // strides of n3 and k1 in a transform buffer
+constexpr int kBuf = 8 * kS1;             // double2 per transform buffer (1352)
+constexpr int kP3First = kGT - 2 * kNC;   // first pass-3 thread of a group (80)
 constexpr int kN = kNB, kRows = kNB / 2 + 2, kPairs = kRows / 2, kTile = 2 * kNB;
 constexpr uint32_t kTileBytes = kTile * sizeof(double), kTileBytes32 = kTile * sizeof(float);
 constexpr uint32_t kStageBytes = 2 * kTileBytes + 2 * kTileBytes32;
 constexpr size_t kStageDoubles = kStageBytes / sizeof(double);
 constexpr int kStages = 2, kTabMax = 64;
-constexpr size_t kSmem2 = 128 + (size_t)(G::TW1 + G::TW2) * sizeof(double2) + (size_t)kStages * kStageBytes +
+constexpr size_t kSmem2 = 128 + (size_t)kGroupTw * sizeof(double2) + (size_t)kStages * kStageBytes +
                           (size_t)kGroups * kBuf * sizeof(double2) + kTabMax * (2 * sizeof(double) + 4 * sizeof(int));
 static_assert(kSmem2 <= 232448, "group kernel shared memory exceeds the 227 KB per-CTA limit");
+static_assert(kP3First >= 64 && kP3First % 2 == 0, "pass 3 pairs adjacent lanes behind the pass-2 warps");
 
 struct Rows2Params {
     const double* D;       // [nplanes][kRows][N]
@@ -48,11 +60,11 @@ struct Rows2Params {
     const float* D32;
     const float* T32;
     double2* Y;            // [nplanes][nlam][kNC][kRows]
-    const uint16_t* kcol;  // [nlam][kNC] row-pass frequencies kept per PSF
+    const GroupP3* p3;     // [nlam][2 kNC] pass-3 outputs per wavelength
     const double* dmin;    // [nplanes][kRows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
-    const float2* tw32;    // single-precision twiddles (global memory, L1-resident)
+    const float2* tw32;    // [20][7] single-precision pass-1 twiddles (global memory, L1-resident)
     int* next_item;
     double cut, grade, f32_min;
     int nplanes, nlam;
@@ -62,109 +74,108 @@ __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGT) : "memory");
 }
 
-// Layout buf[k1 * S + m * 21 + n3] of passes 1/2 and who does what in passes 2 and 3.  Both element
-// types are 16 bytes (a double2, or the packed pair Z2): a quarter-warp must hit 8 distinct
-// 16-byte slots, which S = 172, pass 2 with n3 fastest along the lanes and pass 3 with k2 fastest
-// achieve.
-template <class Z>
-struct Lay {
-    static_assert(sizeof(Z) == 16, "the layouts are chosen for 16-byte elements");
-    static constexpr int S = 172;
-    __device__ static int p2_k1(int b) { return b / 20; }
-    __device__ static int p2_n3(int b) { return b % 20; }
-    __device__ static int p3_k1(int b) { return b >> 3; }
-    __device__ static int p3_k2(int b) { return b & 7; }
-};
-
-// twiddles of a thread's two radix-8 butterflies: w_N^(b k1) and w_160^(n3 k2), k = 1..7: the FP64
-// ones from the shared-memory tables, the single-precision ones from the L1-resident float table
+// pass-1 twiddles of a thread, w_160^(n2 k1), k1 = 1..7: the FP64 ones from the shared-memory table,
+// the single-precision ones from the L1-resident float table
 struct TwSmem {
-    const double2* p1;  // + (j*7)*32 + t, shared memory
-    const double2* p2;  // + n3
-    __device__ __forceinline__ double2 tw1(int k1) const { return p1[(k1 - 1) * 32]; }
-    __device__ __forceinline__ double2 tw2(int k2) const { return p2[(k2 - 1) * kR3]; }
+    const double2* p1;  // + n2 * 7, shared memory
+    __device__ __forceinline__ double2 tw1(int k1) const { return p1[k1 - 1]; }
 };
-struct TwMem32Pair {   // the same float table, broadcast into both halves of a packed pair
+struct TwMem32Pair {   // the float table, broadcast into both halves of a packed pair
     const float2* p1;
-    const float2* p2;
-    __device__ __forceinline__ Z2 tw1(int k1) const { return ztw<Z2>(__ldg(p1 + (k1 - 1) * 32)); }
-    __device__ __forceinline__ Z2 tw2(int k2) const { return ztw<Z2>(__ldg(p2 + (k2 - 1) * kR3)); }
+    __device__ __forceinline__ Z2 tw1(int k1) const { return ztw<Z2>(__ldg(p1 + (k1 - 1))); }
 };
 
-// one half (wavelength) of a packed pair / the value itself, as FP64
-__device__ __forceinline__ double2 half_of(const Z2& m, int h) {
-    return h ? make_double2((double)m.x.v.y, (double)m.y.v.y) : make_double2((double)m.x.v.x, (double)m.y.v.x);
+// pass-3 accumulator of one output: FP64, or one half (wavelength) of a packed pair in FP32
+struct Acc64 {
+    double2 a;
+    __device__ __forceinline__ void init(const double2& v, int) { a = v; }
+    __device__ __forceinline__ void step(const double2& v, const GroupP3& e, int) {
+        a = make_double2(fma(a.x, e.w.x, fma(-a.y, e.w.y, v.x)), fma(a.x, e.w.y, fma(a.y, e.w.x, v.y)));
+    }
+    __device__ __forceinline__ double2 value() const { return a; }
+};
+struct Acc32 {
+    float2 a;
+    __device__ __forceinline__ void init(const Z2& v, int h) { a = h ? make_float2(v.x.v.y, v.y.v.y) : make_float2(v.x.v.x, v.y.v.x); }
+    __device__ __forceinline__ void step(const Z2& v, const GroupP3& e, int h) {
+        const float vx = h ? v.x.v.y : v.x.v.x, vy = h ? v.y.v.y : v.y.v.x;
+        a = make_float2(fmaf(a.x, e.w32.x, fmaf(-a.y, e.w32.y, vx)), fmaf(a.x, e.w32.y, fmaf(a.y, e.w32.x, vy)));
+    }
+    __device__ __forceinline__ double2 value() const { return make_double2((double)a.x, (double)a.y); }
+};
+template <class Z> struct AccOf { using type = Acc64; };
+template <> struct AccOf<Z2> { using type = Acc32; };
+
+__device__ __forceinline__ GroupP3 load_p3(const GroupP3* e) {
+    const uint4* q = reinterpret_cast<const uint4*>(e);
+    const uint4 a = __ldg(q), c = __ldg(q + 1);
+    GroupP3 r;
+    r.w = make_double2(__hiloint2double((int)a.y, (int)a.x), __hiloint2double((int)a.w, (int)a.z));
+    r.w32 = make_float2(__uint_as_float(c.x), __uint_as_float(c.y));
+    r.base = c.z;
+    r.col = c.w;
+    return r;
 }
-__device__ __forceinline__ double2 half_of(const double2& m, int) { return m; }
 
 // passes of one transform on the group's buffer, from the eight pass-1 inputs of every thread to the
-// store of the 80 sampled frequencies of both rows (see the file header for the index maps).
+// store of the kept frequencies of both rows (see the file header for the index maps).  eA / outA:
+// pass-3 table and destination of the transform (of half A of a packed pair), eB / outB: of half B.
 template <class Z, class TW>
 __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
-                                                const uint16_t* __restrict__ kidx, double2* __restrict__ out,
-                                                const uint16_t* __restrict__ kidx2 = nullptr,
-                                                double2* __restrict__ out2 = nullptr) {
-    using L = Lay<Z>;
-    constexpr int S = L::S;
-    const int n2 = b / 20, n3 = b % 20;
+                                                const GroupP3* __restrict__ eA, double2* __restrict__ outA,
+                                                const GroupP3* __restrict__ eB = nullptr,
+                                                double2* __restrict__ outB = nullptr) {
     dft8(x);
-    group_bar(grp);   // the gather of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
-    buf[n2 * 21 + n3] = x[0];
-#pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S + n2 * 21 + n3] = cmul(x[k1], tw.tw1(k1));
-    group_bar(grp);
-    // ---- pass 2: radix-8 over n2 (thread = (k1, n3), see Lay), twiddle, in place
+    group_bar(grp);   // pass 3 of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
     {
-        Z* col = buf + L::p2_k1(b) * S + L::p2_n3(b);
+        Z* dst = buf + (b & 7) * kS2 + (b >> 3);
+        dst[0] = x[0];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) x[m] = col[m * 21];
-        dft8(x);
-        col[0] = x[0];
-#pragma unroll
-        for (int k2 = 1; k2 < 8; ++k2) col[k2 * 21] = cmul(x[k2], tw.tw2(k2));
+        for (int k1 = 1; k1 < 8; ++k1) dst[k1 * kS1] = cmul(x[k1], tw.tw1(k1));
     }
     group_bar(grp);
-    // ---- pass 3: radix-20 over n3 by the first two warps of the group (rows k2-fastest: a quarter-
-    // warp hits eight distinct 16-byte slots), natural-order output.  Splitting it into 4 x 5
-    // sub-passes over all 160 threads was measured SLOWER (3.63 vs 3.38 ms per chunk: one more
-    // barrier and one more trip through shared memory cost more than the idle warps), and so was
-    // giving a row to two threads (even / odd outputs, each a 10-point transform of the folded
-    // row: 3.36 vs 3.21 ms - every row is then read twice, and the kernel is shared-memory-bound).
+    // ---- pass 2: radix-20 over n2 by the first two warps of the group (rows n3-fastest: a quarter-warp
+    // hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier inside.
+    // Giving a row to two threads or splitting the radix-20 into sub-passes over all 160 threads was
+    // measured slower for the full transform.
+    GroupP3 ea, eb;
     if (b < 64) {
-        const int k2 = L::p3_k2(b), k1 = L::p3_k1(b);
+        Z* row = buf + (b >> 3) * kS1 + (b & 7) * kS2;
         Z z[20];
-        const Z* row = buf + k1 * S + k2 * 21;
 #pragma unroll
         for (int i = 0; i < 20; ++i) z[i] = row[i];
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + kGroups + grp) : "memory");   // all rows read before any is overwritten
         dft_r3<kR3>(z);
-        const int k0 = k1 + 8 * k2;
 #pragma unroll
-        for (int k3 = 0; k3 < 20; ++k3) {
-            const int k = k0 + 64 * k3;
-            buf[k + (k >> 3)] = z[k3];
-        }
+        for (int i = 0; i < 20; ++i) row[i] = z[i];
+    } else if (b >= kP3First) {
+        // the pass-3 threads fetch their table entries meanwhile
+        ea = load_p3(eA + (b - kP3First));
+        if (outB != nullptr) eb = load_p3(eB + (b - kP3First));
     }
     group_bar(grp);
-    // ---- gather + untangle + store: thread pair (2y, 2y+1) holds X[k_y] and X[-k_y] of kept frequency y
-    // (the first three warps; warp 2 runs with its upper half clamped so that the shuffle is warp-wide);
-    // a packed pair does it once per wavelength (each has its own frequencies), reading its half
-    if (b < 96) {
+    // ---- pass 3 (pruned): one needed output per thread, Horner in w_N^k over n3; then the pair (X[k],
+    // X[-k]) on adjacent lanes untangles the two packed real rows; a packed pair does it once per
+    // wavelength (each has its own frequencies), reading its half
+    if (b >= kP3First) {
+        const unsigned mask = (b < 96) ? 0xffff0000u : 0xffffffffu;   // warp 2 of the group: upper half only
+        using A = typename AccOf<Z>::type;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const uint16_t* kx = h ? kidx2 : kidx;
-            double2* o = h ? out2 : out;
-            if (h && o == nullptr) break;   // a single transform, or a pair with only one wavelength
-            const int y = min(b >> 1, kNC - 1);
-            const int k = (int)__ldg(kx + y);
-            const int kk = (b & 1) ? (kN - k) % kN : k;
-            const double2 mine = half_of(buf[kk + (kk >> 3)], h);
+            if (h && outB == nullptr) break;   // a single transform, or a pair with only one wavelength
+            const GroupP3& e = h ? eb : ea;
+            double2* o = h ? outB : outA;
+            const Z* r = buf + e.base;
+            A acc;
+            acc.init(r[7 * kS2], h);
+#pragma unroll
+            for (int n3 = 6; n3 >= 0; --n3) acc.step(r[n3 * kS2], e, h);
+            const double2 mine = acc.value();
             double2 other;
-            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-            other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-            if (!(b & 1) && b < 2 * kNC) {
+            other.x = __shfl_xor_sync(mask, mine.x, 1);
+            other.y = __shfl_xor_sync(mask, mine.y, 1);
+            if (!(b & 1)) {
                 const double2 za = mine, zb = other;
-                st_global_256(o + (size_t)y * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                st_global_256(o + (size_t)e.col * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
                               make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
             }
         }
@@ -180,9 +191,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     volatile int* la_of = item_of + kStages;   // sorted positions [0, la) dead, [la, lb) single precision,
     volatile int* lb_of = la_of + kStages;     //   [lb, nlam) FP64 (as in hot_rows_kernel)
     volatile int* ns_of = lb_of + kStages;     // stream slots of the item: pairs of single-precision units, FP64 units
-    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);
-    double2* tw2 = tw1 + G::TW1;
-    double* ring = reinterpret_cast<double*>(tw2 + G::TW2);
+    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);   // [20][7] pass-1 twiddles w_160^(n2 k1)
+    double* ring = reinterpret_cast<double*>(tw1 + kGroupTw);
     double2* bufs = reinterpret_cast<double2*>(ring + (size_t)kStages * kStageDoubles);
     double* tab_c = reinterpret_cast<double*>(bufs + (size_t)kGroups * kBuf);
     double* tab_rc = tab_c + kTabMax;
@@ -235,9 +245,9 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         }
     };
 
-    for (int i = threadIdx.x; i < G::TW1 + G::TW2; i += blockDim.x) tw1[i] = g_tw[i];
-    const TwSmem twr{tw1 + ((b >> 5) * 7) * 32 + (b & 31), tw2 + Lay<double2>::p2_n3(b)};
-    const TwMem32Pair twp{p.tw32 + ((b >> 5) * 7) * 32 + (b & 31), p.tw32 + G::TW1 + Lay<Z2>::p2_n3(b)};
+    for (int i = threadIdx.x; i < kGroupTw; i += blockDim.x) tw1[i] = g_tw[i];
+    const TwSmem twr{tw1 + (b >> 3) * 7};
+    const TwMem32Pair twp{p.tw32 + (b >> 3) * 7};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
@@ -350,8 +360,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
                 }
             }
-            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.kcol + (size_t)lamA * kNC, out_of(lamA),
-                            p.kcol + (size_t)lamB * kNC, two ? out_of(lamB) : nullptr);
+            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.p3 + (size_t)lamA * 2 * kNC, out_of(lamA),
+                            p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr);
         } else {
             // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
             const int pos = lb + (slot - npair);
@@ -378,7 +388,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
                 }
             }
-            group_transform(x, buf, twr, b, grp, p.kcol + (size_t)lam * kNC, out_of(lam));
+            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam));
         }
         base += kGroups;
     }
@@ -389,14 +399,14 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
 int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
     if (c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "the group row kernel is dim-1280 only");
     if (int rc = ensure_dynamic_smem(c, group_rows_kernel, kSmem2)) return rc;
-    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_kcol, c->d_dmin, c->d_csort,
-                  c->d_lorder, c->d_tw32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
+    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_p3, c->d_dmin, c->d_csort,
+                  c->d_lorder, c->d_twg32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * kPairs) grid = nplanes * kPairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
     int rc = hot_event(c, 0, s);
     if (rc) return rc;
-    group_rows_kernel<<<grid, kGroups * kGT, kSmem2, s>>>(p, c->d_tw);
+    group_rows_kernel<<<grid, kGroups * kGT, kSmem2, s>>>(p, c->d_twg);
     PSFR_LAUNCH_CHECK(c);
     if ((rc = hot_event(c, 1, s))) return rc;
     c->hot_launches += 1;

@@ -21,6 +21,18 @@ struct Dim {
     static constexpr int Rows = NH + 2;      // half-plane rows 0..N/2 plus one zero pad row
     static constexpr int Pairs = Rows / 2;   // row pairs
 };
+// Group row kernel (psfr_hot2.cu): pass-1 twiddle table w_160^(n2 k1) [20][7] and the per-(wavelength,
+// thread) record of the pruned third pass: output k of thread t, as the Horner base w = w_N^k (FP64 and
+// FP32), the offset of its row (k mod 8)*169 + (k div 8) mod 20 in the transform buffer and the kept
+// frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k]) belongs to.
+constexpr int kGroupTw = 20 * 7;
+struct alignas(16) GroupP3 {
+    double2 w;
+    float2 w32;
+    uint32_t base;
+    uint32_t col;
+};
+static_assert(sizeof(GroupP3) == 32, "GroupP3 is loaded as two 16-byte words");
 constexpr int kAO = PSFR_AO_DIM;        // 80
 constexpr int kPSF = PSFR_PSF_DIM;      // 40
 constexpr int kNS = 2 * kPSF;           // 80 sampled rows / columns per PSF
@@ -72,6 +84,9 @@ struct Ctx {
     float* d_dphi32 = nullptr;   // [max_planes][rows][N] single-precision copy of d_dphi (dim 1280: block grading + FP32 row pairs)
     float* d_otf32 = nullptr;    // [rows][N] single-precision copy of d_otf
     float2* d_tw32 = nullptr;    // twiddles of d_tw rounded to single precision
+    double2* d_twg = nullptr;    // [kGroupTw] pass-1 twiddles of the group row kernel (dim 1280)
+    float2* d_twg32 = nullptr;   // the same in single precision
+    GroupP3* d_p3 = nullptr;     // [max_lambda][2 kNC] pass-3 records of the group row kernel
     double* d_csort = nullptr;   // [max_lambda] c_lambda in descending order (unit classes of the row kernel)
     int* d_lorder = nullptr;     // [max_lambda] wavelength index of sorted position i
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel

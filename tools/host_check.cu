@@ -120,61 +120,48 @@ int check_packed(double tol) {
     return maxerr / maxref < tol ? 0 : 1;
 }
 
-// The 160-thread group transform of csrc/psfr_hot2.cu (one transform held in a 1440-entry
-// complex buffer, three radix passes): same index maps and buffer layouts, threads run one
-// after the other with the group barriers as phase boundaries.
+// The 160-thread group transform of csrc/psfr_hot2.cu (one transform held in a 1352-entry complex
+// buffer: radix-8 and radix-20 passes, then the pruned third pass - Horner in w_N^k over the eight
+// values of row (k mod 8, (k div 8) mod 20)): same index maps and buffer layout, threads run one after
+// the other with the group barriers as phase boundaries; every output k is checked.
 int check_group() {
-    constexpr int R3 = 20;
-    using G = FftGeom<R3>;
-    const int N = G::N;
-    std::vector<double2> tw1, tw2;
-    build_twiddles<R3>(tw1, tw2);
-    std::vector<double2> x(N), buf(1440);
+    constexpr int R3 = 20, S2 = 21, S1 = 8 * S2 + 1;
+    const int N = 1280;
+    std::vector<double2> x(N), buf(8 * S1);
     srand(3);
     for (auto& z : x) z = make_double2(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
-    for (int b = 0; b < 160; ++b) {                       // pass 1
-        const int n2 = b / 20, n3 = b % 20, j = b >> 5, t = b & 31;
+    for (int b = 0; b < 160; ++b) {                       // pass 1: thread b = n2*8 + n3
+        const int n2 = b >> 3, n3 = b & 7;
         double2 v[8];
         for (int n1 = 0; n1 < 8; ++n1) v[n1] = x[n1 * 160 + b];
         dft8(v);
-        buf[n2 * 21 + n3] = v[0];
-        for (int k1 = 1; k1 < 8; ++k1) buf[k1 * 172 + n2 * 21 + n3] = cmul(v[k1], tw1[(j * 7 + (k1 - 1)) * 32 + t]);
+        buf[n3 * S2 + n2] = v[0];
+        for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S1 + n3 * S2 + n2] = cmul(v[k1], unit_root((long long)n2 * k1, 160));
     }
-    for (int b = 0; b < 160; ++b) {                       // pass 2
-        const int k1 = b / 20, n3 = b % 20;
-        double2* col = buf.data() + k1 * 172 + n3;
-        double2 v[8];
-        for (int m = 0; m < 8; ++m) v[m] = col[m * 21];
-        dft8(v);
-        col[0] = v[0];
-        for (int k2 = 1; k2 < 8; ++k2) col[k2 * 21] = cmul(v[k2], tw2[(k2 - 1) * R3 + n3]);
-    }
-    std::vector<std::vector<double2>> z(64, std::vector<double2>(20));
-    for (int b = 0; b < 64; ++b) {                        // pass 3: all rows read, then written
-        const int k2 = b & 7, k1 = b >> 3;
-        for (int i = 0; i < 20; ++i) z[b][i] = buf[k1 * 172 + k2 * 21 + i];
-    }
-    for (int b = 0; b < 64; ++b) {
-        const int k2 = b & 7, k1 = b >> 3;
-        dft_r3<R3>(z[b].data());
-        for (int k3 = 0; k3 < 20; ++k3) {
-            const int k = k1 + 8 * k2 + 64 * k3;
-            buf[k + (k >> 3)] = z[b][k3];
-        }
+    for (int b = 0; b < 64; ++b) {                        // pass 2: thread (k1, n3), radix-20 over n2, in place
+        double2* row = buf.data() + (b >> 3) * S1 + (b & 7) * S2;
+        double2 z[20];
+        for (int i = 0; i < 20; ++i) z[i] = row[i];
+        dft_r3<R3>(z);
+        for (int i = 0; i < 20; ++i) row[i] = z[i];
     }
     double maxerr = 0, maxref = 0;
-    for (int k = 0; k < N; k += 3) {
+    for (int k = 0; k < N; ++k) {                         // pass 3 for every output
+        const double2 w = unit_root(k, N);
+        const double2* r = buf.data() + (k & 7) * S1 + (k >> 3) % 20;
+        double2 acc = r[7 * S2];
+        for (int n3 = 6; n3 >= 0; --n3) acc = cadd(cmul(acc, w), r[n3 * S2]);
+        if (k % 3) continue;
         long double sr = 0, si = 0;
         for (int n = 0; n < N; ++n) {
-            double2 w = unit_root((long long)n * k, N);
-            sr += (long double)x[n].x * w.x - (long double)x[n].y * w.y;
-            si += (long double)x[n].x * w.y + (long double)x[n].y * w.x;
+            double2 wn = unit_root((long long)n * k, N);
+            sr += (long double)x[n].x * wn.x - (long double)x[n].y * wn.y;
+            si += (long double)x[n].x * wn.y + (long double)x[n].y * wn.x;
         }
-        const double2 g = buf[k + (k >> 3)];
-        maxerr = fmax(maxerr, fabs((double)(sr - g.x)) + fabs((double)(si - g.y)));
+        maxerr = fmax(maxerr, fabs((double)(sr - acc.x)) + fabs((double)(si - acc.y)));
         maxref = fmax(maxref, fabs((double)sr) + fabs((double)si));
     }
-    printf("N=%d group transform max err %.3e (ref scale %.3e) rel %.3e\n", N, maxerr, maxref, maxerr / maxref);
+    printf("N=%d group transform (pruned pass 3) max err %.3e (ref scale %.3e) rel %.3e\n", N, maxerr, maxref, maxerr / maxref);
     return maxerr / maxref < 1e-14 ? 0 : 1;
 }
 
