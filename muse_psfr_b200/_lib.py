@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpsfr_b200.so')
+if os.environ.get('PSFR_LIB_TAG'):      # tuning experiments only: a variant built by build.py with the same tag
+    LIB_PATH = LIB_PATH.replace('.so', '_%s.so' % os.environ['PSFR_LIB_TAG'])
 
 # record layouts (keep in sync with include/psfr.h)
 DRAW_R0, DRAW_L0, DRAW_FITC, DRAW_ALPHA_TT, DRAW_NLAYERS = 0, 1, 2, 3, 4

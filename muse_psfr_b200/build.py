@@ -36,12 +36,15 @@ def _stale():
 
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the C-ABI shared library.
-    PSFR_NVCC_EXTRA (environment) appends flags, e.g. -DPSFR_HOT_BLK=4 for tuning experiments."""
-    if not force and not _stale():
+    Tuning experiments: PSFR_NVCC_EXTRA (environment) appends flags, e.g. -DPSFR_FIT_MINBLOCKS=3, and
+    PSFR_LIB_TAG=x writes the variant to libpsfr_b200_x.so (loaded with PSFR_LIB_TAG=x as well)."""
+    tag = os.environ.get('PSFR_LIB_TAG', '')
+    lib = LIB if not tag else LIB.replace('.so', '_%s.so' % tag)
+    if not force and not tag and not _stale():
         return LIB
     nvcc = _nvcc()
     extra = os.environ.get('PSFR_NVCC_EXTRA', '').split()
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' + ('_' + tag if tag else ''))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -56,9 +59,9 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError('nvcc failed on %s' % src)
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [nvcc, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

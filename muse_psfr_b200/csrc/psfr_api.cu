@@ -50,13 +50,16 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
     return PSFR_OK;
 }
 
-// Pass-3 records of the group row kernel (psfr_hot2.cu) for one wavelength: thread pair (2q, 2q+1) gets
-// a kept frequency k and its mirror.  A thread reads buf[base + 21 n3], n3 = 0..7, i.e. 16-byte slot
-// (slot0 + 5 n3) mod 8 with slot0 = (k mod 8 + (k div 8) mod 20) mod 8: the pairs are dealt greedily so
-// that the eight threads of a quarter-warp have as few equal slot0 as the frequency set allows.
-static void group_p3_table(const uint16_t* kc, GroupP3* out) {
+// Pass-3 records and pass-2 row masks of the group row kernel (psfr_hot2.cu) for one wavelength: thread
+// pair (2q, 2q+1) gets a kept frequency k and its mirror.  A thread reads buf[base + 21 n3], n3 = 0..7,
+// i.e. 16-byte slot (slot0 + 5 n3) mod 8 with slot0 = (k mod 8 + (k div 8) mod 20) mod 8: the pairs are
+// dealt greedily so that the eight threads of a quarter-warp have as few equal slot0 as the frequency set
+// allows (measured: 1.6 wavefronts per quarter-warp load instead of 1; reading every row from its own
+// rotated start would make it exactly 1, but the extra selects made the kernel slower).
+static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
     auto slot0 = [](int k) { return ((k & 7) + ((k >> 3) % 20)) & 7; };
     bool used[kNC] = {false};
+    for (int k1 = 0; k1 < 8; ++k1) mask[k1] = 0;
     int q = 0;
     for (int g = 0; g < kNC / 4; ++g) {          // quarter-warps of four pairs
         int cnt[8] = {0};
@@ -81,6 +84,7 @@ static void group_p3_table(const uint16_t* kc, GroupP3* out) {
                 e.w32 = make_float2((float)e.w.x, (float)e.w.y);
                 e.base = (uint32_t)((k & 7) * 169 + (k >> 3) % 20);
                 e.col = (uint32_t)best;
+                mask[k & 7] |= 1u << ((k >> 3) % 20);
             }
         }
     }
@@ -176,10 +180,14 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
                                  "frequencies", lam_host[l], x, (int)kxl[x]);
     }
     std::vector<GroupP3> p3;
+    std::vector<uint32_t> p2m;
     if (c->d_p3) {
         p3.resize((size_t)nlam * 2 * kNC);
-        for (int l = 0; l < nlam; ++l) group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC);
+        p2m.resize((size_t)nlam * 8);
+        for (int l = 0; l < nlam; ++l)
+            group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC, p2m.data() + (size_t)l * 8);
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_p3, p3.data(), p3.size() * sizeof(GroupP3), cudaMemcpyHostToDevice, s));
+        PSFR_CUDA(c, cudaMemcpyAsync(c->d_p2mask, p2m.data(), p2m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     }
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_kcol, kc.data(), kc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     PSFR_CUDA(c, cudaMemcpyAsync(c->d_xmap, xm.data(), xm.size() * sizeof(short2), cudaMemcpyHostToDevice, s));
@@ -267,7 +275,7 @@ void psfr_destroy(psfr_ctx* c) {
     cudaFree(c->d_fit); cudaFree(c->d_poly); cudaFree(c->d_dmin); cudaFree(c->d_counter);
     cudaFree(c->d_twc); cudaFree(c->d_wsamp); cudaFree(c->d_wcol); cudaFree(c->d_kcol); cudaFree(c->d_xmap); cudaFree(c->d_khat_tt); cudaFree(c->d_khat_mu);
     cudaFree(c->d_cube3); cudaFree(c->d_fit2);
-    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_twg); cudaFree(c->d_twg32); cudaFree(c->d_p3); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
+    cudaFree(c->d_dphi32); cudaFree(c->d_otf32); cudaFree(c->d_tw32); cudaFree(c->d_twg); cudaFree(c->d_twg32); cudaFree(c->d_p3); cudaFree(c->d_p2mask); cudaFree(c->d_csort); cudaFree(c->d_lorder); cudaFree(c->d_kaddr);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -358,6 +366,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         CK(dev_alloc(c, &c->d_twg, (size_t)kGroupTw));
         CK(dev_alloc(c, &c->d_twg32, (size_t)kGroupTw));
         CK(dev_alloc(c, &c->d_p3, LM * 2 * kNC));
+        CK(dev_alloc(c, &c->d_p2mask, LM * 8));
     }
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNC * kRows));

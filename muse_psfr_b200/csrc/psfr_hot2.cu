@@ -33,6 +33,14 @@
 #include "fast_exp.cuh"
 #include "tma.cuh"
 
+// tuning switches of the experiments recorded in DESIGN.md 3.11
+#ifndef PSFR_G_LDS128
+#define PSFR_G_LDS128 1    // pass 3 of a packed pair reads whole 16-byte elements (else the two floats of its half)
+#endif
+#ifndef PSFR_G_P2MASK
+#define PSFR_G_P2MASK 1    // pass 2 stores only the rows pass 3 reads
+#endif
+
 namespace psfr {
 
 int hot_event(Ctx* c, int which, cudaStream_t s);
@@ -60,7 +68,8 @@ struct Rows2Params {
     const float* D32;
     const float* T32;
     double2* Y;            // [nplanes][nlam][kNC][kRows]
-    const GroupP3* p3;     // [nlam][2 kNC] pass-3 outputs per wavelength
+    const GroupP3* p3;     // [nlam][2 kNC] pass-3 records per wavelength
+    const uint32_t* rows;  // [nlam][8] rows (k1, k2) pass 3 reads
     const double* dmin;    // [nplanes][kRows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
@@ -85,46 +94,66 @@ struct TwMem32Pair {   // the float table, broadcast into both halves of a packe
     __device__ __forceinline__ Z2 tw1(int k1) const { return ztw<Z2>(__ldg(p1 + (k1 - 1))); }
 };
 
-// pass-3 accumulator of one output: FP64, or one half (wavelength) of a packed pair in FP32
-struct Acc64 {
-    double2 a;
-    __device__ __forceinline__ void init(const double2& v, int) { a = v; }
-    __device__ __forceinline__ void step(const double2& v, const GroupP3& e, int) {
-        a = make_double2(fma(a.x, e.w.x, fma(-a.y, e.w.y, v.x)), fma(a.x, e.w.y, fma(a.y, e.w.x, v.y)));
-    }
-    __device__ __forceinline__ double2 value() const { return a; }
+// Pass 3 of one thread: X[k] = sum_n3 v[n3] w^n3 by Horner's rule over the eight values of its row -
+// FP64 for a double2 buffer, FP32 on one half (wavelength) of a packed-pair buffer.  The thread's record
+// is fetched (fetch_p3) while pass 2 runs: its L2 latency must not sit between the barriers.
+struct P3Reg {
+    double2 w;
+    float2 w32;
+    int base, col;
 };
-struct Acc32 {
-    float2 a;
-    __device__ __forceinline__ void init(const Z2& v, int h) { a = h ? make_float2(v.x.v.y, v.y.v.y) : make_float2(v.x.v.x, v.y.v.x); }
-    __device__ __forceinline__ void step(const Z2& v, const GroupP3& e, int h) {
-        const float vx = h ? v.x.v.y : v.x.v.x, vy = h ? v.y.v.y : v.y.v.x;
-        a = make_float2(fmaf(a.x, e.w32.x, fmaf(-a.y, e.w32.y, vx)), fmaf(a.x, e.w32.y, fmaf(a.y, e.w32.x, vy)));
-    }
-    __device__ __forceinline__ double2 value() const { return make_double2((double)a.x, (double)a.y); }
-};
-template <class Z> struct AccOf { using type = Acc64; };
-template <> struct AccOf<Z2> { using type = Acc32; };
-
-__device__ __forceinline__ GroupP3 load_p3(const GroupP3* e) {
-    const uint4* q = reinterpret_cast<const uint4*>(e);
+__device__ __forceinline__ P3Reg fetch_p3(const GroupP3* __restrict__ tab) {
+    const uint4* q = reinterpret_cast<const uint4*>(tab);
     const uint4 a = __ldg(q), c = __ldg(q + 1);
-    GroupP3 r;
-    r.w = make_double2(__hiloint2double((int)a.y, (int)a.x), __hiloint2double((int)a.w, (int)a.z));
-    r.w32 = make_float2(__uint_as_float(c.x), __uint_as_float(c.y));
-    r.base = c.z;
-    r.col = c.w;
-    return r;
+    P3Reg e;
+    e.w = make_double2(__hiloint2double((int)a.y, (int)a.x), __hiloint2double((int)a.w, (int)a.z));
+    e.w32 = make_float2(__uint_as_float(c.x), __uint_as_float(c.y));
+    e.base = (int)c.z;
+    e.col = (int)c.w;
+    return e;
+}
+__device__ __forceinline__ double2 pass3(const double2* buf, const P3Reg& e, int) {
+    const double2* r = buf + e.base;
+    double2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = r[i * kS2];
+    double2 a = v[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i)
+        a = make_double2(fma(a.x, e.w.x, fma(-a.y, e.w.y, v[i].x)), fma(a.x, e.w.y, fma(a.y, e.w.x, v[i].y)));
+    return a;
+}
+__device__ __forceinline__ double2 pass3(const Z2* buf, const P3Reg& e, int h) {
+    float2 v[8];
+#if PSFR_G_LDS128
+    const float4* r = reinterpret_cast<const float4*>(buf + e.base);   // (x.A, x.B, y.A, y.B) per element
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 q = r[i * kS2];
+        v[i] = h ? make_float2(q.y, q.w) : make_float2(q.x, q.z);
+    }
+#else
+    const float* r = reinterpret_cast<const float*>(buf + e.base) + h;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(r[i * kS2 * 4], r[i * kS2 * 4 + 2]);
+#endif
+    float2 a = v[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i)
+        a = make_float2(fmaf(a.x, e.w32.x, fmaf(-a.y, e.w32.y, v[i].x)), fmaf(a.x, e.w32.y, fmaf(a.y, e.w32.x, v[i].y)));
+    return make_double2((double)a.x, (double)a.y);
 }
 
 // passes of one transform on the group's buffer, from the eight pass-1 inputs of every thread to the
-// store of the kept frequencies of both rows (see the file header for the index maps).  eA / outA:
-// pass-3 table and destination of the transform (of half A of a packed pair), eB / outB: of half B.
+// store of the kept frequencies of both rows (see the file header for the index maps).  tabA / outA /
+// rowsA: pass-3 records, destination and needed-row masks of the transform (of half A of a packed
+// pair), tabB / outB / rowsB: of half B.
 template <class Z, class TW>
 __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
-                                                const GroupP3* __restrict__ eA, double2* __restrict__ outA,
-                                                const GroupP3* __restrict__ eB = nullptr,
-                                                double2* __restrict__ outB = nullptr) {
+                                                const GroupP3* __restrict__ tabA, double2* __restrict__ outA,
+                                                const uint32_t* __restrict__ rowsA,
+                                                const GroupP3* __restrict__ tabB = nullptr, double2* __restrict__ outB = nullptr,
+                                                const uint32_t* __restrict__ rowsB = nullptr) {
     dft8(x);
     group_bar(grp);   // pass 3 of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
     {
@@ -135,47 +164,51 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
     }
     group_bar(grp);
     // ---- pass 2: radix-20 over n2 by the first two warps of the group (rows n3-fastest: a quarter-warp
-    // hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier inside.
-    // Giving a row to two threads or splitting the radix-20 into sub-passes over all 160 threads was
-    // measured slower for the full transform.
-    GroupP3 ea, eb;
+    // hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier inside -
+    // and only the outputs k2 that pass 3 will read are stored (the mask is the same for the eight
+    // lanes of a quarter-warp: whole wavefronts are saved).  Giving a row to two threads or splitting
+    // the radix-20 into sub-passes over all 160 threads was measured slower for the full transform
+    // (DESIGN.md 3.11).
     if (b < 64) {
         Z* row = buf + (b >> 3) * kS1 + (b & 7) * kS2;
         Z z[20];
 #pragma unroll
         for (int i = 0; i < 20; ++i) z[i] = row[i];
         dft_r3<kR3>(z);
+#if PSFR_G_P2MASK
+        uint32_t need = __ldg(rowsA + (b >> 3));
+        if (rowsB != nullptr) need |= __ldg(rowsB + (b >> 3));
+#pragma unroll
+        for (int i = 0; i < 20; ++i)
+            if ((need >> i) & 1) row[i] = z[i];
+#else
 #pragma unroll
         for (int i = 0; i < 20; ++i) row[i] = z[i];
-    } else if (b >= kP3First) {
-        // the pass-3 threads fetch their table entries meanwhile
-        ea = load_p3(eA + (b - kP3First));
-        if (outB != nullptr) eb = load_p3(eB + (b - kP3First));
+#endif
+    }
+    // the pass-3 threads fetch their records meanwhile
+    P3Reg ea, eb;
+    if (b >= kP3First) {
+        ea = fetch_p3(tabA + (b - kP3First));
+        if (outB != nullptr) eb = fetch_p3(tabB + (b - kP3First));
     }
     group_bar(grp);
-    // ---- pass 3 (pruned): one needed output per thread, Horner in w_N^k over n3; then the pair (X[k],
-    // X[-k]) on adjacent lanes untangles the two packed real rows; a packed pair does it once per
-    // wavelength (each has its own frequencies), reading its half
+    // ---- pass 3 (pruned): one needed output per thread; then the pair (X[k], X[-k]) on adjacent lanes
+    // untangles the two packed real rows; a packed pair does it once per wavelength (each has its own
+    // frequencies), reading its half
     if (b >= kP3First) {
         const unsigned mask = (b < 96) ? 0xffff0000u : 0xffffffffu;   // warp 2 of the group: upper half only
-        using A = typename AccOf<Z>::type;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h && outB == nullptr) break;   // a single transform, or a pair with only one wavelength
-            const GroupP3& e = h ? eb : ea;
             double2* o = h ? outB : outA;
-            const Z* r = buf + e.base;
-            A acc;
-            acc.init(r[7 * kS2], h);
-#pragma unroll
-            for (int n3 = 6; n3 >= 0; --n3) acc.step(r[n3 * kS2], e, h);
-            const double2 mine = acc.value();
+            const double2 mine = pass3(buf, h ? eb : ea, h);
             double2 other;
             other.x = __shfl_xor_sync(mask, mine.x, 1);
             other.y = __shfl_xor_sync(mask, mine.y, 1);
             if (!(b & 1)) {
                 const double2 za = mine, zb = other;
-                st_global_256(o + (size_t)e.col * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                st_global_256(o + (size_t)(h ? eb.col : ea.col) * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
                               make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
             }
         }
@@ -361,7 +394,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 }
             }
             group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.p3 + (size_t)lamA * 2 * kNC, out_of(lamA),
-                            p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr);
+                            p.rows + lamA * 8, p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr,
+                            p.rows + lamB * 8);
         } else {
             // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
             const int pos = lb + (slot - npair);
@@ -388,7 +422,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
                 }
             }
-            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam));
+            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam), p.rows + lam * 8);
         }
         base += kGroups;
     }
@@ -399,7 +433,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
 int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
     if (c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "the group row kernel is dim-1280 only");
     if (int rc = ensure_dynamic_smem(c, group_rows_kernel, kSmem2)) return rc;
-    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_p3, c->d_dmin, c->d_csort,
+    Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_p3, c->d_p2mask, c->d_dmin, c->d_csort,
                   c->d_lorder, c->d_twg32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
     if (grid > nplanes * kPairs) grid = nplanes * kPairs;

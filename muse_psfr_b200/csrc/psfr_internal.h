@@ -21,10 +21,12 @@ struct Dim {
     static constexpr int Rows = NH + 2;      // half-plane rows 0..N/2 plus one zero pad row
     static constexpr int Pairs = Rows / 2;   // row pairs
 };
-// Group row kernel (psfr_hot2.cu): pass-1 twiddle table w_160^(n2 k1) [20][7] and the per-(wavelength,
-// thread) record of the pruned third pass: output k of thread t, as the Horner base w = w_N^k (FP64 and
-// FP32), the offset of its row (k mod 8)*169 + (k div 8) mod 20 in the transform buffer and the kept
-// frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k]) belongs to.
+// Group row kernel (psfr_hot2.cu): pass-1 twiddle table w_160^(n2 k1) [20][7], and per wavelength
+//  * the record of the pruned third pass for thread t: output k (a kept frequency or its mirror), as the
+//    Horner base w = w_N^k in FP64 and FP32, the offset of its row (k mod 8)*169 + (k div 8) mod 20 in
+//    the transform buffer and the kept frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k])
+//    belongs to;
+//  * the rows (k1, k2) pass 3 reads, as one 20-bit mask per k1: pass 2 stores only those.
 constexpr int kGroupTw = 20 * 7;
 struct alignas(16) GroupP3 {
     double2 w;
@@ -87,6 +89,7 @@ struct Ctx {
     double2* d_twg = nullptr;    // [kGroupTw] pass-1 twiddles of the group row kernel (dim 1280)
     float2* d_twg32 = nullptr;   // the same in single precision
     GroupP3* d_p3 = nullptr;     // [max_lambda][2 kNC] pass-3 records of the group row kernel
+    uint32_t* d_p2mask = nullptr; // [max_lambda][8] rows (k1, k2) that pass 3 reads
     double* d_csort = nullptr;   // [max_lambda] c_lambda in descending order (unit classes of the row kernel)
     int* d_lorder = nullptr;     // [max_lambda] wavelength index of sorted position i
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel

@@ -147,10 +147,16 @@ int check_group() {
     }
     double maxerr = 0, maxref = 0;
     for (int k = 0; k < N; ++k) {                         // pass 3 for every output
-        const double2 w = unit_root(k, N);
+        // as the kernel: the row is read from n3 = rot on (register i holds n3 = (i + rot) & 7), Horner with the
+        // ratio w, or w^-7 where the exponent wraps, and the common factor w^rot at the end
+        const int rot = (5 * k + 3) & 7;
+        const double2 w = unit_root(k, N), wm7 = unit_root(-7LL * k, N), wrot = unit_root((long long)rot * k, N);
         const double2* r = buf.data() + (k & 7) * S1 + (k >> 3) % 20;
-        double2 acc = r[7 * S2];
-        for (int n3 = 6; n3 >= 0; --n3) acc = cadd(cmul(acc, w), r[n3 * S2]);
+        double2 v[8];
+        for (int i = 0; i < 8; ++i) v[i] = r[((i + rot) & 7) * S2];
+        double2 acc = v[7];
+        for (int i = 6; i >= 0; --i) acc = cadd(cmul(acc, i == 7 - rot ? wm7 : w), v[i]);
+        acc = cmul(acc, wrot);
         if (k % 3) continue;
         long double sr = 0, si = 0;
         for (int n = 0; n < N; ++n) {
