@@ -201,7 +201,7 @@ def run_reference(args):
             'config': workload_config(args),
             'cpu_baseline': {'value': value, 'unit': 'PSF/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'PSF/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -490,7 +490,7 @@ def run_gpu(args):
                                           'psfrec.py (%.1f s)' % (what, dt)}
     if g.world == 1 and not args.no_configs:
         line['other_configs'] = other_configs(g, args, psfrec, _lib)
-    print(json.dumps(line))
+    emit(line)
     g.close()
 
 
@@ -612,8 +612,24 @@ def run_config(args):
         v, dt = cpu_throughput(jobs, cores if args.config != 3 else 1)
         line['cpu_baseline'] = {'value': v, 'unit': 'PSF/s', 'cores': cores if args.config != 3 else 1, 'kind': 'port',
                                 'sample': '%s, numpy oracle port of psfrec.py (%.1f s)' % (what, dt)}
-    print(json.dumps(line))
+    emit(line)
     g.close()
+
+
+_JSON_FD = [1]
+
+
+def own_stdout():
+    """Keep stdout to the ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL and
+    other native libraries print banners straight to fd 1) and the line goes to the saved descriptor."""
+    sys.stdout.flush()
+    _JSON_FD[0] = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD[0], (json.dumps(line) + '\n').encode())
 
 
 def main():
@@ -636,6 +652,7 @@ def main():
     ap.add_argument('--row-kernel', type=int, default=None, dest='row_kernel', help='PSFR_OPT_ROW_KERNEL override (tuning)')
     ap.add_argument('--exp-cut', type=float, default=None, dest='exp_cut', help='PSFR_OPT_EXP_CUT override (tuning)')
     args = ap.parse_args()
+    own_stdout()
     if args.impl == 'reference':
         run_reference(args)
     elif args.config != 4:
