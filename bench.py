@@ -409,12 +409,13 @@ def run_gpu(args):
     h_cube = torch.empty((nd, nlam, 40, 40), dtype=torch.float64, pin_memory=True)
     h_fit = torch.empty((nd, nlam, _lib.FIT_NPAR), dtype=torch.float64, pin_memory=True)
     gathered = {}
+    h_fit_all = torch.empty((total, nlam, _lib.FIT_NPAR), dtype=torch.float64, pin_memory=True) if strong and g.rank == 0 else None
 
     def step_e2e():
         if strong:
             # every rank: parameters on the host -> its block on its GPU -> its cube block into pinned host
             # memory; the fit records go device -> rank 0 over NCCL and from there to the host
-            fit_all, _, _ = sharding.compute_psf_sharded(LBDA, seeing, GL, L0, h=h, out_cube=h_cube, want_sum=False,
+            fit_all, _, _ = sharding.compute_psf_sharded(LBDA, seeing, GL, L0, h=h, out_cube=h_cube, want_sum=False, fit_host=h_fit_all,
                                                          device=g.local, max_planes=args.max_planes, stream=g.stream)
             gathered['fit'] = fit_all
         else:

@@ -50,10 +50,11 @@ def _comm_device(dist):
     return torch.device('cpu')
 
 
-def gather_grid(local, ndraw, nlam, dst=0):
+def gather_grid(local, ndraw, nlam, dst=0, host_out=None):
     """Gather per-rank blocks `local` [nd_loc, nl_loc, ...] (numpy array or torch tensor, host or
     device) into the full [ndraw, nlam, ...] array on rank `dst` (numpy); None elsewhere.  With
-    nccl the blocks travel device to device (NVLink) and rank `dst` does one device -> host copy."""
+    nccl the blocks travel device to device (NVLink) and rank `dst` does one device -> host copy -
+    into `host_out` (a pinned torch tensor of the full shape) when given."""
     import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
@@ -76,6 +77,11 @@ def gather_grid(local, ndraw, nlam, dst=0):
         n = (d1 - d0) * (l1 - l0)
         if n:
             full[d0:d1, l0:l1] = bufs[r][:n * width].reshape((d1 - d0, l1 - l0) + tail)
+    if host_out is not None:
+        host_out.copy_(full, non_blocking=True)
+        if full.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        return host_out.numpy()
     return full.cpu().numpy()
 
 
@@ -92,7 +98,8 @@ def allreduce_sum(arr):
 
 
 def compute_psf_sharded(lbda, seeing, GL, L0, h=(100, 10000), npsflin=1, three_lgs_mode=False,
-                        want_cube=False, compute_fn=None, out_cube=None, want_sum=True, **kwargs):
+                        want_cube=False, compute_fn=None, out_cube=None, want_sum=True, fit_host=None,
+                        **kwargs):
     """compute_psf_batch over the ranks of the current process group.
 
     Every rank passes the FULL parameter arrays, processes its own (draw, wavelength) block on its
@@ -101,7 +108,8 @@ def compute_psf_sharded(lbda, seeing, GL, L0, h=(100, 10000), npsflin=1, three_l
     records stay on the device until rank 0 has gathered them.  ``out_cube`` (optional, pinned host
     tensor or numpy array [nd_loc, nl_loc, 40, 40]) receives this rank's own cube block - the sharded
     output a caller keeps local when only the fits are gathered.  ``compute_fn`` (tests) replaces the
-    CUDA call; extra keyword arguments go to it.  ``want_sum=False`` skips the cube sum (then None)."""
+    CUDA call; extra keyword arguments go to it.  ``want_sum=False`` skips the cube sum (then None); ``fit_host``
+    (rank 0: pinned tensor [ndraw, nl, 16]) receives the gathered fit records without a pageable copy."""
     dist = _dist()
     world = dist.get_world_size() if dist else 1
     rank = dist.get_rank() if dist else 0
@@ -138,6 +146,6 @@ def compute_psf_sharded(lbda, seeing, GL, L0, h=(100, 10000), npsflin=1, three_l
             local_sum = cube.sum(dim=0) if hasattr(cube, 'data_ptr') else np.asarray(cube).sum(axis=0)
             part[l0:l1] = local_sum.cpu().numpy() if hasattr(local_sum, 'cpu') else local_sum
         cube_sum = allreduce_sum(part)
-    fit_all = gather_grid(fit, n, nl)
+    fit_all = gather_grid(fit, n, nl, host_out=fit_host if rank == 0 else None)
     cube_all = gather_grid(cube, n, nl) if want_cube else None
     return fit_all, cube_all, cube_sum
