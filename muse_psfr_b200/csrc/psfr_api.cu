@@ -51,15 +51,17 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
 }
 
 // Pass-3 records and pass-2 row masks of the group row kernel (psfr_hot2.cu) for one wavelength: thread
-// pair (2q, 2q+1) gets a kept frequency k and its mirror.  A thread reads buf[base + 21 n3], n3 = 0..7,
-// i.e. 16-byte slot (slot0 + 5 n3) mod 8 with slot0 = (k mod 8 + (k div 8) mod 20) mod 8: the pairs are
+// pair (2q, 2q+1) gets a kept frequency k and its mirror.  A thread reads buf[base + kGS2 n3], n3 = 0..7,
+// i.e. 16-byte slot (slot0 + kGS2 n3) mod 8 with slot0 = (k1 + k2) mod 8 (kGS1 = 1 mod 8): the pairs are
 // dealt greedily so that the eight threads of a quarter-warp have as few equal slot0 as the frequency set
 // allows (measured: 1.6 wavefronts per quarter-warp load instead of 1; reading every row from its own
 // rotated start would make it exactly 1, but the extra selects made the kernel slower).
 static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
-    auto slot0 = [](int k) { return ((k & 7) + ((k >> 3) % 20)) & 7; };
+    auto k1_of = [](int k) { return k % kG1; };
+    auto k2_of = [](int k) { return (k / kG1) % kG2; };
+    auto slot0 = [&](int k) { return (k1_of(k) + k2_of(k)) & 7; };
     bool used[kNC] = {false};
-    for (int k1 = 0; k1 < 8; ++k1) mask[k1] = 0;
+    for (int k1 = 0; k1 < kGMaskStride; ++k1) mask[k1] = 0;
     int q = 0;
     for (int g = 0; g < kNC / 4; ++g) {          // quarter-warps of four pairs
         int cnt[8] = {0};
@@ -82,9 +84,9 @@ static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
                 GroupP3& e = out[2 * q + sgn];
                 e.w = unit_root(k, kNB);
                 e.w32 = make_float2((float)e.w.x, (float)e.w.y);
-                e.base = (uint32_t)((k & 7) * 169 + (k >> 3) % 20);
+                e.base = (uint32_t)(k1_of(k) * kGS1 + k2_of(k));
                 e.col = (uint32_t)best;
-                mask[k & 7] |= 1u << ((k >> 3) % 20);
+                mask[k1_of(k)] |= 1u << k2_of(k);
             }
         }
     }
@@ -183,9 +185,9 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
     std::vector<uint32_t> p2m;
     if (c->d_p3) {
         p3.resize((size_t)nlam * 2 * kNC);
-        p2m.resize((size_t)nlam * 8);
+        p2m.resize((size_t)nlam * kGMaskStride);
         for (int l = 0; l < nlam; ++l)
-            group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC, p2m.data() + (size_t)l * 8);
+            group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC, p2m.data() + (size_t)l * kGMaskStride);
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_p3, p3.data(), p3.size() * sizeof(GroupP3), cudaMemcpyHostToDevice, s));
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_p2mask, p2m.data(), p2m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     }
@@ -366,7 +368,7 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         CK(dev_alloc(c, &c->d_twg, (size_t)kGroupTw));
         CK(dev_alloc(c, &c->d_twg32, (size_t)kGroupTw));
         CK(dev_alloc(c, &c->d_p3, LM * 2 * kNC));
-        CK(dev_alloc(c, &c->d_p2mask, LM * 8));
+        CK(dev_alloc(c, &c->d_p2mask, LM * kGMaskStride));
     }
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNC * kRows));
@@ -416,11 +418,11 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     if (c->d_twg) {
         std::vector<double2> twg(kGroupTw);
         std::vector<float2> twg32(kGroupTw);
-        for (int n2 = 0; n2 < 20; ++n2)
-            for (int k1 = 1; k1 < 8; ++k1) {
+        for (int n2 = 0; n2 < kG2; ++n2)
+            for (int k1 = 1; k1 < kG1; ++k1) {
                 const double2 w = unit_root((long long)n2 * k1, 160);
-                twg[n2 * 7 + k1 - 1] = w;
-                twg32[n2 * 7 + k1 - 1] = make_float2((float)w.x, (float)w.y);
+                twg[n2 * (kG1 - 1) + k1 - 1] = w;
+                twg32[n2 * (kG1 - 1) + k1 - 1] = make_float2((float)w.x, (float)w.y);
             }
         CKC(cudaMemcpy(c->d_twg, twg.data(), twg.size() * sizeof(double2), cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_twg32, twg32.data(), twg32.size() * sizeof(float2), cudaMemcpyHostToDevice));

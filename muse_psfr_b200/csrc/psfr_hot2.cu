@@ -4,28 +4,31 @@
 //
 //   hot_rows_kernel : one WARP = one 1280-point transform, 40 points per lane in registers,
 //                     ~70 KB of unrolled code per unit, 8 warps per SM (253 registers);
-//   group_rows_kernel: one GROUP of 160 threads = one transform that lives in shared memory
-//                     (21.6 KB), two full radix passes (8, 20) and a PRUNED third one that evaluates
+//   group_rows_kernel: one GROUP of 128 threads = one transform that lives in shared memory
+//                     (21.9 KB), two full radix passes (10, 16) and a PRUNED third one that evaluates
 //                     only the 80 outputs the column pass needs (the 40 kept frequencies and their
-//                     mirrors), a few KB of code, 15 warps per SM.
+//                     mirrors), a few KB of code, four groups = 16 warps per SM.
 //
-// Index maps:  n = n1*160 + n2*8 + n3,  k = k1 + 8*k2 + 160*k3  (n1, n3, k1, k3 < 8; n2, k2 < 20).
-//   pass 1 : thread b = n2*8 + n3 evaluates its own eight inputs x[n1*160 + b] (both rows:
-//            exp(-c D) * T, graded like hot_rows_kernel but per 32-cell segment), radix-8 over
-//            n1, times w_160^(n2 k1)                    -> buf[k1*169 + n3*21 + n2]
-//   pass 2 : threads (k1, n3) < 64: radix-20 over n2 (Good-Thomas 4 x 5, no twiddles), in place
-//                                                        -> buf[k1*169 + n3*21 + k2]
-//   pass 3 : threads 80..159, one per needed output k: X[k] = sum_n3 buf[k1*169 + n3*21 + k2] (w_N^k)^n3
+// Index maps (psfr_internal.h; kG1 x kG2 x 8 = 10 x 16 x 8, or 8 x 20 x 8 with PSFR_G_GEOM = 0):
+//   n = n1*kGThreads + n2*8 + n3,  k = k1 + kG1*k2 + 160*k3.
+//   pass 1 : thread b = n2*8 + n3 evaluates its own kG1 inputs x[n1*kGThreads + b] (both rows:
+//            exp(-c D) * T, graded like hot_rows_kernel but per 32-cell segment), radix-kG1 over
+//            n1, times w_160^(n2 k1)                    -> buf[k1*kGS1 + n3*kGS2 + n2]
+//   pass 2 : threads (k1, n3) < 8 kG1: radix-kG2 over n2 (no twiddles), in place, storing only the
+//            rows pass 3 reads                          -> buf[k1*kGS1 + n3*kGS2 + k2]
+//   pass 3 : the last 80 threads, one per needed output k: X[k] = sum_n3 buf[k1*kGS1 + n3*kGS2 + k2] (w_N^k)^n3
 //            by Horner's rule - the twiddle between passes 2 and 3 and the radix-8 phase are one
 //            power series in w_N^k, held per (wavelength, thread) in a table (set_lambda_tables);
 //            adjacent threads hold X[k], X[-k]: one shuffle, untangle the two real rows, one
 //            32-byte store per kept frequency.
 // The full transform's third pass (64 x radix-20, natural-order dump, gather of 160 values) took two
-// more trips through shared memory and the kernel is shared-memory-bound (profiles/).
-// Strides 169 / 21 make the 16-byte accesses of passes 1 and 2 conflict-free (a quarter-warp hits
-// eight distinct 16-byte slots); in pass 3 the slot of a thread is (k1 + k2 + 5 n3) mod 8 and the host
-// orders the outputs so that the eight threads of a quarter-warp differ in (k1 + k2) mod 8 wherever
-// the wavelength's frequency set allows it.
+// more trips through shared memory and the kernel was shared-memory-bound (profiles/).
+// The 10 x 16 x 8 split keeps 128 / 80 / 80 of a group's 128 threads busy in the three passes (8 x 20 x 8:
+// 160 / 64 / 80 of 160) and fits four transforms per SM within 128 registers per thread.
+// Strides kGS1 / kGS2 (odd n3 stride, kGS1 = 1 mod 8) make the 16-byte accesses of passes 1 and 2
+// conflict-free (a quarter-warp hits eight distinct 16-byte slots); in pass 3 the slot of a thread is
+// (k1 + k2 + kGS2 n3) mod 8 and the host orders the outputs so that the eight threads of a quarter-warp
+// differ in (k1 + k2) mod 8 wherever the wavelength's frequency set allows it.
 //
 // Row pairs below exp(-f32_min) run the same passes in single precision, two wavelengths at a time
 // as the halves of one packed transform (Z2, warp_fft.cuh); each half has its own pass-3 outputs.
@@ -47,11 +50,12 @@ int hot_event(Ctx* c, int which, cudaStream_t s);
 
 namespace {
 
-constexpr int kGroups = 3;                // transforms in flight per CTA
-constexpr int kGT = 160;                  // threads per group
-constexpr int kS2 = 21, kS1 = 8 * kS2 + 1;   // strides of n3 and k1 in a transform buffer
-constexpr int kBuf = 8 * kS1;             // double2 per transform buffer (1352)
-constexpr int kP3First = kGT - 2 * kNC;   // first pass-3 thread of a group (80)
+constexpr int kGroups = kGGroups;         // transforms in flight per CTA
+constexpr int kGT = kGThreads;            // threads per group
+constexpr int kS2 = kGS2, kS1 = kGS1;     // strides of n3 and k1 in a transform buffer
+constexpr int kBuf = kG1 * kS1;           // double2 per transform buffer
+constexpr int kP2Threads = 8 * kG1;       // rows (k1, n3) of pass 2
+constexpr int kP3First = kGT - 2 * kNC;   // first pass-3 thread of a group
 constexpr int kN = kNB, kRows = kNB / 2 + 2, kPairs = kRows / 2, kTile = 2 * kNB;
 constexpr uint32_t kTileBytes = kTile * sizeof(double), kTileBytes32 = kTile * sizeof(float);
 constexpr uint32_t kStageBytes = 2 * kTileBytes + 2 * kTileBytes32;
@@ -60,7 +64,17 @@ constexpr int kStages = 2, kTabMax = 64;
 constexpr size_t kSmem2 = 128 + (size_t)kGroupTw * sizeof(double2) + (size_t)kStages * kStageBytes +
                           (size_t)kGroups * kBuf * sizeof(double2) + kTabMax * (2 * sizeof(double) + 4 * sizeof(int));
 static_assert(kSmem2 <= 232448, "group kernel shared memory exceeds the 227 KB per-CTA limit");
-static_assert(kP3First >= 64 && kP3First % 2 == 0, "pass 3 pairs adjacent lanes behind the pass-2 warps");
+static_assert(kP3First >= 0 && kP3First % 32 == 16, "pass 3 starts in the upper half of a warp (shuffle mask below)");
+static_assert(kGT % 32 == 0 && kGroups * kGT <= 1024, "groups are made of whole warps");
+
+// radix-R butterfly of a thread's R values, natural order in and out
+template <int R, class Z>
+__device__ __forceinline__ void dft_any(Z* x) {
+    static_assert(R == 8 || R == 10 || R == 16 || R == 20, "unsupported pass radix");
+    if constexpr (R == 8) dft8(x);
+    else if constexpr (R == 16) dft16(x);
+    else dft_r3<R>(x);
+}
 
 struct Rows2Params {
     const double* D;       // [nplanes][kRows][N]
@@ -73,7 +87,7 @@ struct Rows2Params {
     const double* dmin;    // [nplanes][kRows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
-    const float2* tw32;    // [20][7] single-precision pass-1 twiddles (global memory, L1-resident)
+    const float2* tw32;    // [kG2][kG1 - 1] single-precision pass-1 twiddles (global memory, L1-resident)
     int* next_item;
     double cut, grade, f32_min;
     int nplanes, nlam;
@@ -83,10 +97,10 @@ __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGT) : "memory");
 }
 
-// pass-1 twiddles of a thread, w_160^(n2 k1), k1 = 1..7: the FP64 ones from the shared-memory table,
+// pass-1 twiddles of a thread, w_160^(n2 k1), k1 = 1..kG1-1: the FP64 ones from the shared-memory table,
 // the single-precision ones from the L1-resident float table
 struct TwSmem {
-    const double2* p1;  // + n2 * 7, shared memory
+    const double2* p1;  // + n2 * (kG1 - 1), shared memory
     __device__ __forceinline__ double2 tw1(int k1) const { return p1[k1 - 1]; }
 };
 struct TwMem32Pair {   // the float table, broadcast into both halves of a packed pair
@@ -149,41 +163,39 @@ __device__ __forceinline__ double2 pass3(const Z2* buf, const P3Reg& e, int h) {
 // rowsA: pass-3 records, destination and needed-row masks of the transform (of half A of a packed
 // pair), tabB / outB / rowsB: of half B.
 template <class Z, class TW>
-__device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw, int b, int grp,
+__device__ __forceinline__ void group_transform(Z (&x)[kG1], Z* buf, const TW& tw, int b, int grp,
                                                 const GroupP3* __restrict__ tabA, double2* __restrict__ outA,
                                                 const uint32_t* __restrict__ rowsA,
                                                 const GroupP3* __restrict__ tabB = nullptr, double2* __restrict__ outB = nullptr,
                                                 const uint32_t* __restrict__ rowsB = nullptr) {
-    dft8(x);
+    dft_any<kG1>(x);
     group_bar(grp);   // pass 3 of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
     {
         Z* dst = buf + (b & 7) * kS2 + (b >> 3);
         dst[0] = x[0];
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) dst[k1 * kS1] = cmul(x[k1], tw.tw1(k1));
+        for (int k1 = 1; k1 < kG1; ++k1) dst[k1 * kS1] = cmul(x[k1], tw.tw1(k1));
     }
     group_bar(grp);
-    // ---- pass 2: radix-20 over n2 by the first two warps of the group (rows n3-fastest: a quarter-warp
-    // hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier inside -
-    // and only the outputs k2 that pass 3 will read are stored (the mask is the same for the eight
-    // lanes of a quarter-warp: whole wavefronts are saved).  Giving a row to two threads or splitting
-    // the radix-20 into sub-passes over all 160 threads was measured slower for the full transform
-    // (DESIGN.md 3.11).
-    if (b < 64) {
+    // ---- pass 2: radix-kG2 over n2 by the first 8 kG1 threads of the group (rows n3-fastest: a quarter-
+    // warp hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier
+    // inside - and only the outputs k2 that pass 3 will read are stored (the mask is the same for the
+    // eight lanes of a quarter-warp: whole wavefronts are saved).
+    if (b < kP2Threads) {
         Z* row = buf + (b >> 3) * kS1 + (b & 7) * kS2;
-        Z z[20];
+        Z z[kG2];
 #pragma unroll
-        for (int i = 0; i < 20; ++i) z[i] = row[i];
-        dft_r3<kR3>(z);
+        for (int i = 0; i < kG2; ++i) z[i] = row[i];
+        dft_any<kG2>(z);
 #if PSFR_G_P2MASK
         uint32_t need = __ldg(rowsA + (b >> 3));
         if (rowsB != nullptr) need |= __ldg(rowsB + (b >> 3));
 #pragma unroll
-        for (int i = 0; i < 20; ++i)
+        for (int i = 0; i < kG2; ++i)
             if ((need >> i) & 1) row[i] = z[i];
 #else
 #pragma unroll
-        for (int i = 0; i < 20; ++i) row[i] = z[i];
+        for (int i = 0; i < kG2; ++i) row[i] = z[i];
 #endif
     }
     // the pass-3 threads fetch their records meanwhile
@@ -197,7 +209,7 @@ __device__ __forceinline__ void group_transform(Z (&x)[8], Z* buf, const TW& tw,
     // untangles the two packed real rows; a packed pair does it once per wavelength (each has its own
     // frequencies), reading its half
     if (b >= kP3First) {
-        const unsigned mask = (b < 96) ? 0xffff0000u : 0xffffffffu;   // warp 2 of the group: upper half only
+        const unsigned mask = (b < kP3First + 16) ? 0xffff0000u : 0xffffffffu;   // first pass-3 warp: upper half only
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h && outB == nullptr) break;   // a single transform, or a pair with only one wavelength
@@ -224,7 +236,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     volatile int* la_of = item_of + kStages;   // sorted positions [0, la) dead, [la, lb) single precision,
     volatile int* lb_of = la_of + kStages;     //   [lb, nlam) FP64 (as in hot_rows_kernel)
     volatile int* ns_of = lb_of + kStages;     // stream slots of the item: pairs of single-precision units, FP64 units
-    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);   // [20][7] pass-1 twiddles w_160^(n2 k1)
+    double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);   // [kG2][kG1 - 1] pass-1 twiddles w_160^(n2 k1)
     double* ring = reinterpret_cast<double*>(tw1 + kGroupTw);
     double2* bufs = reinterpret_cast<double2*>(ring + (size_t)kStages * kStageDoubles);
     double* tab_c = reinterpret_cast<double*>(bufs + (size_t)kGroups * kBuf);
@@ -279,8 +291,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     };
 
     for (int i = threadIdx.x; i < kGroupTw; i += blockDim.x) tw1[i] = g_tw[i];
-    const TwSmem twr{tw1 + (b >> 3) * 7};
-    const TwMem32Pair twp{p.tw32 + (b >> 3) * 7};
+    const TwSmem twr{tw1 + (b >> 3) * (kG1 - 1)};
+    const TwMem32Pair twp{p.tw32 + (b >> 3) * (kG1 - 1)};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
@@ -379,10 +391,10 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
             const int lamA = lam_of(posA), lamB = lam_of(posB);
             const float nA = n2f_of(posA), nB = n2f_of(posB);
             const int cut32 = cut_of(posB);   // c_B <= c_A: an entry below the cut at B is below it at A
-            Z2 x[8];
+            Z2 x[kG1];
 #pragma unroll
-            for (int n1 = 0; n1 < 8; ++n1) {
-                const int n = n1 * 160 + b;
+            for (int n1 = 0; n1 < kG1; ++n1) {
+                const int n = n1 * kGT + b;
                 const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
                 const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
                 if (__all_sync(0xffffffffu, dead)) {
@@ -394,8 +406,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 }
             }
             group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.p3 + (size_t)lamA * 2 * kNC, out_of(lamA),
-                            p.rows + lamA * 8, p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr,
-                            p.rows + lamB * 8);
+                            p.rows + lamA * kGMaskStride, p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr,
+                            p.rows + lamB * kGMaskStride);
         } else {
             // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
             const int pos = lb + (slot - npair);
@@ -405,10 +417,10 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
             const float negc2f = n2f_of(pos);
             const int cut32 = cut_of(pos);
             const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
-            double2 x[8];
+            double2 x[kG1];
 #pragma unroll
-            for (int n1 = 0; n1 < 8; ++n1) {
-                const int n = n1 * 160 + b;
+            for (int n1 = 0; n1 < kG1; ++n1) {
+                const int n = n1 * kGT + b;
                 const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
                 const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
                 const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
@@ -422,7 +434,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
                 }
             }
-            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam), p.rows + lam * 8);
+            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam), p.rows + lam * kGMaskStride);
         }
         base += kGroups;
     }

@@ -21,13 +21,30 @@ struct Dim {
     static constexpr int Rows = NH + 2;      // half-plane rows 0..N/2 plus one zero pad row
     static constexpr int Pairs = Rows / 2;   // row pairs
 };
-// Group row kernel (psfr_hot2.cu): pass-1 twiddle table w_160^(n2 k1) [20][7], and per wavelength
+// Group row kernel (psfr_hot2.cu).  A transform of 1280 points is split as kG1 x kG2 x 8 and belongs to
+// a group of kGThreads = 8 kG2 threads; kGGroups groups share a CTA.  Two geometries are compiled in:
+//   PSFR_G_GEOM 1 (default): 10 x 16 x 8, four groups of 128 threads (16 warps; passes of 128 / 80 / 80 threads)
+//   PSFR_G_GEOM 0          :  8 x 20 x 8, three groups of 160 threads (15 warps; 160 / 64 / 80)
+// Index maps: n = n1*kGThreads + n2*8 + n3,  k = k1 + kG1*k2 + 160*k3.
+// Tables: pass-1 twiddles w_160^(n2 k1) [kG2][kG1 - 1], and per wavelength
 //  * the record of the pruned third pass for thread t: output k (a kept frequency or its mirror), as the
-//    Horner base w = w_N^k in FP64 and FP32, the offset of its row (k mod 8)*169 + (k div 8) mod 20 in
-//    the transform buffer and the kept frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k])
-//    belongs to;
-//  * the rows (k1, k2) pass 3 reads, as one 20-bit mask per k1: pass 2 stores only those.
-constexpr int kGroupTw = 20 * 7;
+//    Horner base w = w_N^k in FP64 and FP32, the offset of its row k1*kGS1 + k2 in the transform buffer and
+//    the kept frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k]) belongs to;
+//  * the rows (k1, k2) pass 3 reads, as one kG2-bit mask per k1: pass 2 stores only those.
+#ifndef PSFR_G_GEOM
+#define PSFR_G_GEOM 1
+#endif
+#if PSFR_G_GEOM == 0
+constexpr int kG1 = 8, kG2 = 20, kGGroups = 3;
+#else
+constexpr int kG1 = 10, kG2 = 16, kGGroups = 4;
+#endif
+constexpr int kGThreads = 8 * kG2;       // threads per group = inputs per pass-1 butterfly stride
+constexpr int kGS2 = kG2 + 1;            // stride of n3 in a transform buffer (odd)
+constexpr int kGS1 = 8 * kGS2 + 1;       // stride of k1
+constexpr int kGroupTw = kG2 * (kG1 - 1);
+constexpr int kGMaskStride = 16;         // uint32 masks per wavelength (kG1 used)
+static_assert(kG1 * kG2 * 8 == kNB && kG1 <= kGMaskStride, "group geometry");
 struct alignas(16) GroupP3 {
     double2 w;
     float2 w32;

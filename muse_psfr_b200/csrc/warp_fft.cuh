@@ -178,6 +178,49 @@ PSFR_HD void dft8(Z* x) {
     x[7] = csub(e3, o3);
 }
 
+// 16-point DFT as 4 x 4 (n = 4a + b, k = ka + 4 kb): radix-4 over a, twiddles w16^(b ka), radix-4 over b
+template <class Z>
+PSFR_HD void dft16(Z* x) {
+    using S = typename ZTraits<Z>::S;
+    const S h = (S)0.70710678118654752440, mh = (S)-0.70710678118654752440;
+    const S c = (S)0.92387953251128675613, s = (S)0.38268343236508977173;   // cos, sin of pi/8
+    const S mc = (S)-0.92387953251128675613, ms = (S)-0.38268343236508977173;
+    Z y[16];   // y[b*4 + ka]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        Z t0 = x[b], t1 = x[4 + b], t2 = x[8 + b], t3 = x[12 + b];
+        dft4(t0, t1, t2, t3);
+        y[b * 4 + 0] = t0;
+        y[b * 4 + 1] = t1;
+        y[b * 4 + 2] = t2;
+        y[b * 4 + 3] = t3;
+    }
+    // v * (wr + i wi) without negations of packed values: re = wr x - wi y, im = wr y + wi x (mwi = -wi)
+#define tw(v, wr, wi, mwi) mkz<Z>(sfma((mwi), (v).y, (wr) * (v).x), sfma((wi), (v).x, (wr) * (v).y))
+    y[1 * 4 + 1] = tw(y[1 * 4 + 1], c, s, ms);                       // w16^1
+    y[1 * 4 + 2] = mkz<Z>(h * (y[1 * 4 + 2].x - y[1 * 4 + 2].y), h * (y[1 * 4 + 2].x + y[1 * 4 + 2].y));   // w16^2
+    y[1 * 4 + 3] = tw(y[1 * 4 + 3], s, c, mc);                       // w16^3
+    y[2 * 4 + 1] = mkz<Z>(h * (y[2 * 4 + 1].x - y[2 * 4 + 1].y), h * (y[2 * 4 + 1].x + y[2 * 4 + 1].y));   // w16^2
+    {
+        const Z v = y[2 * 4 + 2];                                    // w16^4 = i
+        y[2 * 4 + 2] = mkz<Z>(v.y * (S)(-1.0), v.x);
+    }
+    y[2 * 4 + 3] = mkz<Z>(mh * (y[2 * 4 + 3].x + y[2 * 4 + 3].y), h * (y[2 * 4 + 3].x - y[2 * 4 + 3].y));  // w16^6
+    y[3 * 4 + 1] = tw(y[3 * 4 + 1], s, c, mc);                       // w16^3
+    y[3 * 4 + 2] = mkz<Z>(mh * (y[3 * 4 + 2].x + y[3 * 4 + 2].y), h * (y[3 * 4 + 2].x - y[3 * 4 + 2].y));  // w16^6
+    y[3 * 4 + 3] = tw(y[3 * 4 + 3], mc, ms, s);                      // w16^9 = -(c + i s)
+#undef tw
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        Z t0 = y[ka], t1 = y[4 + ka], t2 = y[8 + ka], t3 = y[12 + ka];
+        dft4(t0, t1, t2, t3);
+        x[ka] = t0;
+        x[ka + 4] = t1;
+        x[ka + 8] = t2;
+        x[ka + 12] = t3;
+    }
+}
+
 template <class Z>
 PSFR_HD void dft5(Z& x0, Z& x1, Z& x2, Z& x3, Z& x4) {
     using S = typename ZTraits<Z>::S;

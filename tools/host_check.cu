@@ -1,9 +1,11 @@
 // CPU emulation of the warp FFT in csrc/warp_fft.cuh: runs the same __host__ __device__
 // phase functions lane by lane and compares with a direct O(N^2) DFT.  Build + run:
 //   nvcc -O2 -I muse_psfr_b200/csrc tools/host_check.cu -o /tmp/host_check && /tmp/host_check
+// (add -DPSFR_G_GEOM=0 for the 8 x 20 x 8 geometry of the group transform)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include "psfr_internal.h"
 #include "warp_fft.cuh"
 #include "fft_tables.h"
 using namespace psfr;
@@ -120,43 +122,43 @@ int check_packed(double tol) {
     return maxerr / maxref < tol ? 0 : 1;
 }
 
-// The 160-thread group transform of csrc/psfr_hot2.cu (one transform held in a 1352-entry complex
-// buffer: radix-8 and radix-20 passes, then the pruned third pass - Horner in w_N^k over the eight
-// values of row (k mod 8, (k div 8) mod 20)): same index maps and buffer layout, threads run one after
-// the other with the group barriers as phase boundaries; every output k is checked.
+// The group transform of csrc/psfr_hot2.cu (one transform held in a complex buffer of kG1 * kGS1 entries:
+// radix-kG1 and radix-kG2 passes, then the pruned third pass - Horner in w_N^k over the eight values of
+// row (k mod kG1, (k div kG1) mod kG2)): same index maps and buffer layout, threads run one after the
+// other with the group barriers as phase boundaries; every output k is checked.
+template <int R>
+void dft_host(double2* x) {
+    if (R == 8) dft8(x);
+    else if (R == 16) dft16(x);
+    else dft_r3<(R == 8 || R == 16) ? 20 : R>(x);
+}
 int check_group() {
-    constexpr int R3 = 20, S2 = 21, S1 = 8 * S2 + 1;
+    constexpr int S2 = kGS2, S1 = kGS1, GT = kGThreads;
     const int N = 1280;
-    std::vector<double2> x(N), buf(8 * S1);
+    std::vector<double2> x(N), buf(kG1 * S1);
     srand(3);
     for (auto& z : x) z = make_double2(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
-    for (int b = 0; b < 160; ++b) {                       // pass 1: thread b = n2*8 + n3
+    for (int b = 0; b < GT; ++b) {                        // pass 1: thread b = n2*8 + n3
         const int n2 = b >> 3, n3 = b & 7;
-        double2 v[8];
-        for (int n1 = 0; n1 < 8; ++n1) v[n1] = x[n1 * 160 + b];
-        dft8(v);
+        double2 v[kG1];
+        for (int n1 = 0; n1 < kG1; ++n1) v[n1] = x[n1 * GT + b];
+        dft_host<kG1>(v);
         buf[n3 * S2 + n2] = v[0];
-        for (int k1 = 1; k1 < 8; ++k1) buf[k1 * S1 + n3 * S2 + n2] = cmul(v[k1], unit_root((long long)n2 * k1, 160));
+        for (int k1 = 1; k1 < kG1; ++k1) buf[k1 * S1 + n3 * S2 + n2] = cmul(v[k1], unit_root((long long)n2 * k1, 160));
     }
-    for (int b = 0; b < 64; ++b) {                        // pass 2: thread (k1, n3), radix-20 over n2, in place
+    for (int b = 0; b < 8 * kG1; ++b) {                   // pass 2: thread (k1, n3), radix-kG2 over n2, in place
         double2* row = buf.data() + (b >> 3) * S1 + (b & 7) * S2;
-        double2 z[20];
-        for (int i = 0; i < 20; ++i) z[i] = row[i];
-        dft_r3<R3>(z);
-        for (int i = 0; i < 20; ++i) row[i] = z[i];
+        double2 z[kG2];
+        for (int i = 0; i < kG2; ++i) z[i] = row[i];
+        dft_host<kG2>(z);
+        for (int i = 0; i < kG2; ++i) row[i] = z[i];
     }
     double maxerr = 0, maxref = 0;
     for (int k = 0; k < N; ++k) {                         // pass 3 for every output
-        // as the kernel: the row is read from n3 = rot on (register i holds n3 = (i + rot) & 7), Horner with the
-        // ratio w, or w^-7 where the exponent wraps, and the common factor w^rot at the end
-        const int rot = (5 * k + 3) & 7;
-        const double2 w = unit_root(k, N), wm7 = unit_root(-7LL * k, N), wrot = unit_root((long long)rot * k, N);
-        const double2* r = buf.data() + (k & 7) * S1 + (k >> 3) % 20;
-        double2 v[8];
-        for (int i = 0; i < 8; ++i) v[i] = r[((i + rot) & 7) * S2];
-        double2 acc = v[7];
-        for (int i = 6; i >= 0; --i) acc = cadd(cmul(acc, i == 7 - rot ? wm7 : w), v[i]);
-        acc = cmul(acc, wrot);
+        const double2 w = unit_root(k, N);
+        const double2* r = buf.data() + (k % kG1) * S1 + (k / kG1) % kG2;
+        double2 acc = r[7 * S2];
+        for (int n3 = 6; n3 >= 0; --n3) acc = cadd(cmul(acc, w), r[n3 * S2]);
         if (k % 3) continue;
         long double sr = 0, si = 0;
         for (int n = 0; n < N; ++n) {
@@ -167,7 +169,8 @@ int check_group() {
         maxerr = fmax(maxerr, fabs((double)(sr - acc.x)) + fabs((double)(si - acc.y)));
         maxref = fmax(maxref, fabs((double)sr) + fabs((double)si));
     }
-    printf("N=%d group transform (pruned pass 3) max err %.3e (ref scale %.3e) rel %.3e\n", N, maxerr, maxref, maxerr / maxref);
+    printf("N=%d group transform %d x %d x 8 (pruned pass 3) max err %.3e (ref scale %.3e) rel %.3e\n", N, kG1, kG2,
+           maxerr, maxref, maxerr / maxref);
     return maxerr / maxref < 1e-14 ? 0 : 1;
 }
 
@@ -195,6 +198,23 @@ int main() {
             printf("dft_r3<%d> err %.3e\n", R, me);
             if (me > 1e-11) bad = 1;
         }
+    }
+    {
+        double2 x[16], y[16];
+        for (int i = 0; i < 16; ++i) x[i] = y[i] = make_double2(0.37 * i - 1.3, 0.11 * i * i - 2.1);
+        dft16(y);
+        double me = 0;
+        for (int k = 0; k < 16; ++k) {
+            double sr = 0, si = 0;
+            for (int n = 0; n < 16; ++n) {
+                double2 w = unit_root(n * k, 16);
+                sr += x[n].x * w.x - x[n].y * w.y;
+                si += x[n].x * w.y + x[n].y * w.x;
+            }
+            me = fmax(me, fabs(sr - y[k].x) + fabs(si - y[k].y));
+        }
+        printf("dft16 err %.3e\n", me);
+        if (me > 1e-12) bad = 1;
     }
     bad |= check<20, double2>(1e-14);
     bad |= check<20, float2>(2e-6);
