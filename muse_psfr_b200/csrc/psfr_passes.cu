@@ -240,24 +240,32 @@ struct LoadColumnPadded {
 };
 
 // ------------------------------------------------------------------ storers
-// untangle the two real lines and write them transposed: Bt[plane][y][2rp], [2rp+1]
-template <int NF>
+// untangle the two real lines and write them transposed: Bt[plane][y][2rp], [2rp+1].
+// UPPER = true writes only the frequencies y = 0 and N/2 .. N-1: the column pass of the structure
+// function (LoadHermitianPair / SrcHermitianPair with npair = Pairs) reads rows (a + N/2) % N,
+// a = 0 .. N/2, and nothing else - half of the scattered 32-byte stores of this pass were never read.
+template <int NF, bool UPPER = false>
 struct StoreTransposedPair {
     using D = Dim<NF>;
     double2* Bt;  // [nplanes][N][Rows]
     int npair;
+    __device__ __forceinline__ void put(double2* out, const double* xb, int y) const {
+        const double2 za = nat_get<NF>(xb, y), zb = nat_get<NF>(xb, (D::N - y) % D::N);
+        st_global_256(out + (size_t)y * D::Rows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                      make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+    }
     __device__ void operator()(int f, int lane, const double* xb) const {
         const int plane = f / npair, rp = f % npair;
         double2* out = Bt + (size_t)plane * D::N * D::Rows + 2 * rp;
         // unrolled far enough that a store's data registers are not rewritten while it still
         // sits in the store queue (ncu: long-scoreboard stalls on the first DADD of a trip)
+        if (UPPER) {
 #pragma unroll 10
-        for (int i = 0; i < 40 * NF; ++i) {
-            const int y = lane + 32 * i;
-            const double2 za = nat_get<NF>(xb, y), zb = nat_get<NF>(xb, (D::N - y) % D::N);
-            double2* o = out + (size_t)y * D::Rows;
-            st_global_256(o, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
-                          make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
+            for (int i = 0; i < 20 * NF; ++i) put(out, xb, D::NH + lane + 32 * i);
+            if (lane == 0) put(out, xb, 0);
+        } else {
+#pragma unroll 10
+            for (int i = 0; i < 40 * NF; ++i) put(out, xb, lane + 32 * i);
         }
     }
 };
@@ -400,23 +408,19 @@ __global__ void finalize_otf_kernel(double* t, float* t32, size_t live, size_t t
 template <int NF>
 static int structure_function_t(Ctx* c, int nplanes, cudaStream_t s, bool from_quadrant, int ndir) {
     using D = Dim<NF>;
-    // pass 1: rows of the even part of the PSD -> transposed half spectrum
+    // pass 1: rows of the even part of the PSD -> transposed half spectrum (only the frequencies pass 2 reads)
     const double k = 0.5 * 1000 / (2 * 3.141592653589793);      // rad^2 -> nm^2 (psfrec.py:151), as run_psd
+    const StoreTransposedPair<NF, true> store{c->d_bt, D::Pairs};
     int rc;
     if constexpr (NF == 1) {
         if (from_quadrant)
-            rc = launch_tiled_pass<PSFR_PASS1_WARPS, SrcEvenRowsQuad::kTileBytes, PSFR_PASS1_OVERLAP>(c, SrcEvenRowsQuad{c->d_psdq, c->d_ao, ndir, k * k},
-                                                                   StoreTransposedPair<1>{c->d_bt, D::Pairs},
-                                                                   nplanes * D::Pairs, s);
+            rc = launch_tiled_pass<PSFR_PASS1_WARPS, SrcEvenRowsQuad::kTileBytes, PSFR_PASS1_OVERLAP>(
+                c, SrcEvenRowsQuad{c->d_psdq, c->d_ao, ndir, k * k}, store, nplanes * D::Pairs, s);
         else
-            rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
-                                 nplanes * D::Pairs, s);
+            rc = launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, store, nplanes * D::Pairs, s);
     } else {
-        rc = from_quadrant
-                 ? launch_pass<NF>(c, LoadEvenRowsQuad<NF>{c->d_psdq, c->d_ao, ndir, k * k},
-                                   StoreTransposedPair<NF>{c->d_bt, D::Pairs}, nplanes * D::Pairs, s)
-                 : launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, StoreTransposedPair<NF>{c->d_bt, D::Pairs},
-                                   nplanes * D::Pairs, s);
+        rc = from_quadrant ? launch_pass<NF>(c, LoadEvenRowsQuad<NF>{c->d_psdq, c->d_ao, ndir, k * k}, store, nplanes * D::Pairs, s)
+                           : launch_pass<NF>(c, LoadEvenRows<NF>{c->d_psd}, store, nplanes * D::Pairs, s);
     }
     if (rc) return rc;
     // pass 2: columns -> rows of the transposed structure function, 2/L^2 with L = 16 m (psfrec.py:710,718)
