@@ -11,7 +11,17 @@
 
 namespace psfr {
 
-__device__ __forceinline__ double fast_exp(double x) {
+// Polynomial coefficients in constant memory: as immediates the compiler re-materialises every one of them
+// through two uniform-register moves per use (ncu: UMOV was 16 % of the row kernel's instructions); a
+// constant-bank operand rides along with the DFMA.
+static __constant__ double kExpPoly[11] = {
+    2.5110049204818659793e-8, 2.763265472252779189e-7, 2.7557240887229868596e-6, 0.000024801485441561312966,
+    0.00019841269890076402829, 0.0013888888952352862866, 0.0083333333333195896163, 0.04166666666648795252,
+    0.1666666666666668082, 0.50000000000000184039, 1.0};
+static __constant__ double kExpRed[4] = {1.44269504088896338700e+00, 6755399441055744.0, -6.93147180369123816490e-01,
+                                         -1.90821492927058770002e-10};
+
+__device__ __forceinline__ double fast_exp_imm(double x) {
     const double L2E = 1.44269504088896338700e+00;
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: round-to-nearest integer trick
     const double LN2_HI = 6.93147180369123816490e-01;   // low 21 bits zero: k * LN2_HI is exact
@@ -36,6 +46,22 @@ __device__ __forceinline__ double fast_exp(double x) {
     k = max(k, -1000);
     // p in [0.70, 1.42]: scaling by 2^k is an integer add on the exponent field (no denormals for
     // k >= -1000), which keeps one multiply per evaluation off the FP64 pipe
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// the same evaluation with every constant read from the constant bank
+__device__ __forceinline__ double fast_exp(double x) {
+    const double MAGIC = kExpRed[1];
+    const double kd = fma(x, kExpRed[0], MAGIC);
+    int k = __double2loint(kd);
+    const double kf = kd - MAGIC;
+    double r = fma(kf, kExpRed[2], x);
+    r = fma(kf, kExpRed[3], r);
+    double p = kExpPoly[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, r, kExpPoly[i]);
+    p = fma(p, r, 1.0);
+    k = max(k, -1000);
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 

@@ -199,26 +199,28 @@ __device__ __forceinline__ void group_transform(Z (&x)[kG1], Z* buf, const TW& t
 #endif
     }
     // the pass-3 threads fetch their records meanwhile
+    const bool p3 = b >= kP3First;
     P3Reg ea, eb;
-    if (b >= kP3First) {
+    if (p3) {
         ea = fetch_p3(tabA + (b - kP3First));
         if (outB != nullptr) eb = fetch_p3(tabB + (b - kP3First));
     }
     group_bar(grp);
     // ---- pass 3 (pruned): one needed output per thread; then the pair (X[k], X[-k]) on adjacent lanes
     // untangles the two packed real rows; a packed pair does it once per wavelength (each has its own
-    // frequencies), reading its half
-    if (b >= kP3First) {
-        const unsigned mask = (b < kP3First + 16) ? 0xffff0000u : 0xffffffffu;   // first pass-3 warp: upper half only
+    // frequencies), reading its half.  Whole warps enter (the first pass-3 warp with its lower half idle)
+    // so that the shuffle has a compile-time full mask.
+    if (b >= kP3First - 16) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (h && outB == nullptr) break;   // a single transform, or a pair with only one wavelength
             double2* o = h ? outB : outA;
-            const double2 mine = pass3(buf, h ? eb : ea, h);
+            double2 mine = make_double2(0.0, 0.0);
+            if (p3) mine = pass3(buf, h ? eb : ea, h);
             double2 other;
-            other.x = __shfl_xor_sync(mask, mine.x, 1);
-            other.y = __shfl_xor_sync(mask, mine.y, 1);
-            if (!(b & 1)) {
+            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+            other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+            if (p3 && !(b & 1)) {
                 const double2 za = mine, zb = other;
                 st_global_256(o + (size_t)(h ? eb.col : ea.col) * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
                               make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));

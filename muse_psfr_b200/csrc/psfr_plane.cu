@@ -122,6 +122,11 @@ __device__ __forceinline__ double rcp_pos(double u) {
 // half as long as the library log, whose dependent chain dominated the per-pixel latency of the
 // fitter (the kernel runs one image per warp in a single wave).  Max relative error 3.8e-16
 // against a long-double log1p over [1 + 1e-8, 1e4] (the argument is 1 + rho^2 here).
+// series coefficients 1/23 ... 1/3 and the two words of ln 2 in constant memory (see fast_exp.cuh: immediates
+// cost two uniform-register moves per use)
+static __constant__ double kLogPoly[11] = {1.0 / 23, 1.0 / 21, 1.0 / 19, 1.0 / 17, 1.0 / 15, 1.0 / 13,
+                                           1.0 / 11, 1.0 / 9,  1.0 / 7,  1.0 / 5,  1.0 / 3};
+static __constant__ double kLn2[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
 __device__ __forceinline__ double log_ge1(double u) {
     int hi = __double2hiint(u);
     const int k = (hi - 0x3fe6a09e) >> 20;
@@ -129,21 +134,13 @@ __device__ __forceinline__ double log_ge1(double u) {
     const double m = __hiloint2double(hi, __double2loint(u));
     const double s = (m - 1.0) * rcp_pos(m + 1.0);
     const double z = s * s;
-    double p = 1.0 / 23;
-    p = fma(p, z, 1.0 / 21);
-    p = fma(p, z, 1.0 / 19);
-    p = fma(p, z, 1.0 / 17);
-    p = fma(p, z, 1.0 / 15);
-    p = fma(p, z, 1.0 / 13);
-    p = fma(p, z, 1.0 / 11);
-    p = fma(p, z, 1.0 / 9);
-    p = fma(p, z, 1.0 / 7);
-    p = fma(p, z, 1.0 / 5);
-    p = fma(p, z, 1.0 / 3);
+    double p = kLogPoly[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, z, kLogPoly[i]);
     const double kf = (double)k;
-    double r = fma(s * z, 2.0 * p, kf * 1.90821492927058770002e-10);
+    double r = fma(s * z, 2.0 * p, kf * kLn2[1]);
     r += 2.0 * s;
-    return fma(kf, 6.93147180369123816490e-01, r);
+    return fma(kf, kLn2[0], r);
 }
 
 // one pixel's contribution to the normal equations
