@@ -70,7 +70,7 @@ def workload_config(args):
                             '490-930 nm, dim 1280, npsflin 1, 4 LGS' % (args.draws, NLAM),
                 'draws': args.draws, 'wavelengths': NLAM, 'dim': 1280,
                 'l2': '256 MB buffer rewritten before every step (inside the timed region); per-chunk working set '
-                      '~4 GB >> 126 MB L2'}
+                      '~8 GB >> 126 MB L2'}
     names = {1: 'configs[0]: compute_psf single field (1.0", GL 0.7, L0 25 m), dim 1280, 35 wavelengths',
              2: 'configs[1]: compute_psf_from_sparta, 30 time slices x 35 wavelengths, time-averaged PSF + Moffat fit',
              3: 'configs[2]: npsflin=3 field grid, three-LGS mode, 35 wavelengths',
@@ -642,7 +642,7 @@ def main():
     ap.add_argument('--draws5', type=int, default=64, help='draws of the dim-2560 batch (--config 5 / other_configs)')
     ap.add_argument('--config', type=int, default=4, choices=[1, 2, 3, 4, 5], help='BASELINE config (1-based); 4 = the headline sweep')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'], help='N > 1: shard the sweep (default) or replicate it')
-    ap.add_argument('--max-planes', type=int, default=64, dest='max_planes')
+    ap.add_argument('--max-planes', type=int, default=128, dest='max_planes', help='planes per chunk (the library default)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-configs', action='store_true', help='skip the other_configs leg')

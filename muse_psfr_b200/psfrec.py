@@ -446,7 +446,7 @@ def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs
     dirs = direction_perf(npsflin)
     dim = _check_dim(dim)
     if max_planes is None:
-        max_planes = 64 if dim == _DIM else 16
+        max_planes = 128 if dim == _DIM else 16      # planes per chunk of the fused pipeline (~8 GB of workspace)
     ctx = get_context(max_planes=max(dirs.shape[1], min(max_planes, nd * dirs.shape[1])),
                       max_lambda=max(35, lam.size), device=device, dim=dim)
     if out_fit is None:
