@@ -368,10 +368,16 @@ def run_gpu(args):
     d_fit = torch.empty((nd, nlam, _lib.FIT_NPAR), dtype=torch.float64, device=g.dev)
     hot = {'ms': 0.0, 'n': 0, 'psfs': 0}
 
+    gather_ev = []
+
     def step_device():
         ctx.compute_batch(d_recs, dirs, pos, LBDA, out_cube=d_cube, out_fit=d_fit, stream=g.stream)
         if strong:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
             sharding.gather_grid(d_fit, total, nlam)        # NCCL gather of the fit records + D2H on rank 0
+            ev[1].record()
+            gather_ev.append(ev)
 
     def collect_hot():
         ms, n, psfs = ctx.last_hot_timing()     # CUDA events around every launch of the row kernel
@@ -395,6 +401,7 @@ def run_gpu(args):
     first_timed()
     ms_total = g.timed(step_device, args.steps, 0, after_step=collect_hot)
     launches = ctx.kernel_launches() - launches0
+    gather_ms = float(np.mean([a.elapsed_time(b) for a, b in gather_ev[-args.steps:]])) if gather_ev else None
 
     # ---- the same leg with both precision grades off (everything FP64): 3 steps, same draws
     ms_fp64 = None
@@ -443,6 +450,7 @@ def run_gpu(args):
     fit_last = gathered['fit'] if strong and g.rank == 0 else (h_fit.numpy() if not strong else None)
     finite = bool(np.isfinite(fit_last[:, :, _lib.FIT_FWHM]).all()) if fit_last is not None else None
     nonconv = int((fit_last[:, :, _lib.FIT_ITER] < 0).sum()) if fit_last is not None else None
+    fit_iter = float(np.abs(fit_last[:, :, _lib.FIT_ITER]).mean()) if fit_last is not None else None
 
     if g.rank != 0:
         g.close()
@@ -473,7 +481,7 @@ def run_gpu(args):
                 'd2h_bytes_per_step': int(h_cube.numel() * 8 + (total if strong else nd) * nlam * _lib.FIT_NPAR * 8),
                 'api': 'sharding.compute_psf_sharded' if strong else 'psfrec.compute_psf_batch'},
         'gpu_launches': int(launches),
-        'results_finite': finite, 'fits_not_converged': nonconv,
+        'results_finite': finite, 'fits_not_converged': nonconv, 'fit_iterations_mean': fit_iter,
         'roofline': roofline_block(value / g.world, 1280, nlam, hot['ms'], hot['n'], hot['psfs'], hot_launch,
                                    step_bytes, ms_total / args.steps, nd * nlam),
         'clocks': sampler.summary(),
@@ -482,6 +490,10 @@ def run_gpu(args):
         line['value_allfp64'] = job_psfs * 3 / (ms_fp64 * 1e-3)
     if weak:
         line['weak_scaling'] = weak
+    if gather_ms is not None:
+        line['collective'] = {'op': 'gather of the fit records [draws, 35, 16] f64 to rank 0 (NCCL) + device -> host copy',
+                              'ms_per_step_rank0': gather_ms, 'share_of_step': gather_ms / (ms_total / args.steps),
+                              'bytes': int(total * nlam * _lib.FIT_NPAR * 8)}
     if g.world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         jobs, what = cpu_sample(4, cores)
@@ -528,6 +540,8 @@ def time_config(g, args, psfrec, _lib, cfg, steps=3, warmup=2):
         apply_options(ctx5, argparse.Namespace(grade=None, f32_rows=None, exp_cut=args.exp_cut, row_kernel=None), _lib)
         fn = lambda: psfrec.compute_psf(lam5, 1.0, 0.7, 25.0, verbose=False, dim=2560)   # noqa: E731
         psfs = 100
+    if os.environ.get('PSFR_BENCH_BATCH_ONLY') and cfg == 5:
+        warmup = steps = 1          # profiling runs: go straight to the batch
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
