@@ -56,9 +56,10 @@ static int dev_alloc(Ctx* c, T** p, size_t count) {
 // dealt greedily so that the eight threads of a quarter-warp have as few equal slot0 as the frequency set
 // allows (measured: 1.6 wavefronts per quarter-warp load instead of 1; reading every row from its own
 // rotated start would make it exactly 1, but the extra selects made the kernel slower).
-static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
-    auto k1_of = [](int k) { return k % kG1; };
-    auto k2_of = [](int k) { return (k / kG1) % kG2; };
+static void group_p3_table(const uint16_t* kc, int N, GroupP3* out, uint32_t* mask) {
+    // rows and Horner bases belong to the 1280-point (sub-)transform: output k mod 1280
+    auto k1_of = [](int k) { return (k % kNB) % kG1; };
+    auto k2_of = [](int k) { return ((k % kNB) / kG1) % kG2; };
     auto slot0 = [&](int k) { return (k1_of(k) + k2_of(k)) & 7; };
     bool used[kNC] = {false};
     for (int k1 = 0; k1 < kGMaskStride; ++k1) mask[k1] = 0;
@@ -69,7 +70,7 @@ static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
             int best = -1, best_cost = 1 << 30;
             for (int j = 0; j < kNC; ++j) {
                 if (used[j]) continue;
-                const int k = kc[j], km = (kNB - k) % kNB;
+                const int k = kc[j], km = (N - k) % N;
                 const int a = slot0(k), b = slot0(km);
                 const int cost = cnt[a] + cnt[b] + (a == b && k != km ? 1 : 0);
                 if (cost < best_cost) {
@@ -79,10 +80,11 @@ static void group_p3_table(const uint16_t* kc, GroupP3* out, uint32_t* mask) {
             }
             used[best] = true;
             for (int sgn = 0; sgn < 2; ++sgn) {
-                const int k = sgn ? (kNB - kc[best]) % kNB : kc[best];
+                const int k = sgn ? (N - kc[best]) % N : kc[best];
                 ++cnt[slot0(k)];
                 GroupP3& e = out[2 * q + sgn];
-                e.w = unit_root(k, kNB);
+                e.w = unit_root(k % kNB, kNB);
+                e.wc = unit_root(k, N);
                 e.w32 = make_float2((float)e.w.x, (float)e.w.y);
                 e.base = (uint32_t)(k1_of(k) * kGS1 + k2_of(k));
                 e.col = (uint32_t)best;
@@ -187,7 +189,7 @@ static int set_lambda_tables(Ctx* c, int nlam, const double* lam_host, cudaStrea
         p3.resize((size_t)nlam * 2 * kNC);
         p2m.resize((size_t)nlam * kGMaskStride);
         for (int l = 0; l < nlam; ++l)
-            group_p3_table(kc.data() + (size_t)l * kNC, p3.data() + (size_t)l * 2 * kNC, p2m.data() + (size_t)l * kGMaskStride);
+            group_p3_table(kc.data() + (size_t)l * kNC, kN, p3.data() + (size_t)l * 2 * kNC, p2m.data() + (size_t)l * kGMaskStride);
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_p3, p3.data(), p3.size() * sizeof(GroupP3), cudaMemcpyHostToDevice, s));
         PSFR_CUDA(c, cudaMemcpyAsync(c->d_p2mask, p2m.data(), p2m.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     }
@@ -312,7 +314,6 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
     c->max_planes = max_planes;
     c->max_lambda = max_lambda;
     c->NF = dim / kNB;
-    c->row_kernel = c->NF == 1 ? 2 : 1;   // the group row kernel exists for dim 1280 only
     c->N = dim;
     c->NH = dim / 2;
     c->rows = dim / 2 + 2;
@@ -365,11 +366,11 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
         CK(dev_alloc(c, &c->d_dphi32, P * kRows * kN));
         CK(dev_alloc(c, &c->d_otf32, (size_t)kRows * kN));
         CK(dev_alloc(c, &c->d_tw32, (size_t)FftGeom<kR3>::TW1 + FftGeom<kR3>::TW2));
-        CK(dev_alloc(c, &c->d_twg, (size_t)kGroupTw));
         CK(dev_alloc(c, &c->d_twg32, (size_t)kGroupTw));
-        CK(dev_alloc(c, &c->d_p3, LM * 2 * kNC));
-        CK(dev_alloc(c, &c->d_p2mask, LM * kGMaskStride));
     }
+    CK(dev_alloc(c, &c->d_twg, (size_t)kGroupTw));
+    CK(dev_alloc(c, &c->d_p3, LM * 2 * kNC));
+    CK(dev_alloc(c, &c->d_p2mask, LM * kGMaskStride));
     CK(dev_alloc(c, &c->d_counter, (size_t)16));
     CK(dev_alloc(c, &c->d_ybuf, P * LM * kNC * kRows));
     CK(dev_alloc(c, &c->d_samp, P * LM * kNS * kNS));
@@ -425,7 +426,8 @@ int psfr_create(int device, int dim, int max_planes, int max_lambda, psfr_ctx** 
                 twg32[n2 * (kG1 - 1) + k1 - 1] = make_float2((float)w.x, (float)w.y);
             }
         CKC(cudaMemcpy(c->d_twg, twg.data(), twg.size() * sizeof(double2), cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(c->d_twg32, twg32.data(), twg32.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        if (c->d_twg32)
+            CKC(cudaMemcpy(c->d_twg32, twg32.data(), twg32.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
     {
         std::vector<double2> twc(kNB);
@@ -767,7 +769,6 @@ int psfr_set_option(psfr_ctx* c, int key, double value) {
             return PSFR_OK;
         case PSFR_OPT_ROW_KERNEL:
             if (value != 1.0 && value != 2.0) return set_error(c, PSFR_E_ARG, "row kernel must be 1 or 2 (got %g)", value);
-            if (value == 2.0 && c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "row kernel 2 is dim-1280 only");
             c->row_kernel = (int)value;
             return PSFR_OK;
         case PSFR_OPT_F32_ROWS:

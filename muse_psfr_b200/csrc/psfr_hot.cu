@@ -681,7 +681,7 @@ static int pruned_psf_t(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s) {
     int grid = c->sm_count;
     if (grid > nplanes * D::Pairs) grid = nplanes * D::Pairs;
     int rc;
-    if (NF == 1 && c->row_kernel == 2) {
+    if (c->row_kernel == 2) {
         if ((rc = run_group_rows(c, nplanes, nlam, s))) return rc;
     } else {
         PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));

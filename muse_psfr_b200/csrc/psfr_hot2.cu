@@ -1,6 +1,5 @@
-// Row kernel of the pruned stage B at dim 1280 (PSFR_OPT_ROW_KERNEL = 2, the default; 1 selects
-// hot_rows_kernel of psfr_hot.cu, which also serves dim 2560).  Same work, same stream of units,
-// same ring; what differs is who runs a transform:
+// Row kernel of the pruned stage B (PSFR_OPT_ROW_KERNEL = 2, the default; 1 selects hot_rows_kernel of
+// psfr_hot.cu).  Same work, same stream of units, same ring; what differs is who runs a transform:
 //
 //   hot_rows_kernel : one WARP = one 1280-point transform, 40 points per lane in registers,
 //                     ~70 KB of unrolled code per unit, 8 warps per SM (253 registers);
@@ -32,14 +31,17 @@
 //
 // Row pairs below exp(-f32_min) run the same passes in single precision, two wavelengths at a time
 // as the halves of one packed transform (Z2, warp_fft.cuh); each half has its own pass-3 outputs.
+//
+// dim 2560 (NF = 2): a line is two interleaved 1280-point transforms (even / odd samples) that run one
+// after the other through the same passes; pass 3 keeps F0[k mod 1280] in its registers and finishes
+// X[k] = F0 + w_2560^k F1 after the second.  A ring stage then holds two rows of D and of the
+// telescope OTF in FP64 only (80 KB), which leaves room for three groups; units are all FP64
+// (underflow cut per 32-cell segment, no single-precision grades).
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 #include "tma.cuh"
 
 // tuning switches of the experiments recorded in DESIGN.md 3.11
-#ifndef PSFR_G_LDS128
-#define PSFR_G_LDS128 1    // pass 3 of a packed pair reads whole 16-byte elements (else the two floats of its half)
-#endif
 #ifndef PSFR_G_P2MASK
 #define PSFR_G_P2MASK 1    // pass 2 stores only the rows pass 3 reads
 #endif
@@ -50,22 +52,32 @@ int hot_event(Ctx* c, int which, cudaStream_t s);
 
 namespace {
 
-constexpr int kGroups = kGGroups;         // transforms in flight per CTA
 constexpr int kGT = kGThreads;            // threads per group
 constexpr int kS2 = kGS2, kS1 = kGS1;     // strides of n3 and k1 in a transform buffer
 constexpr int kBuf = kG1 * kS1;           // double2 per transform buffer
 constexpr int kP2Threads = 8 * kG1;       // rows (k1, n3) of pass 2
 constexpr int kP3First = kGT - 2 * kNC;   // first pass-3 thread of a group
-constexpr int kN = kNB, kRows = kNB / 2 + 2, kPairs = kRows / 2, kTile = 2 * kNB;
-constexpr uint32_t kTileBytes = kTile * sizeof(double), kTileBytes32 = kTile * sizeof(float);
-constexpr uint32_t kStageBytes = 2 * kTileBytes + 2 * kTileBytes32;
-constexpr size_t kStageDoubles = kStageBytes / sizeof(double);
 constexpr int kStages = 2, kTabMax = 64;
-constexpr size_t kSmem2 = 128 + (size_t)kGroupTw * sizeof(double2) + (size_t)kStages * kStageBytes +
-                          (size_t)kGroups * kBuf * sizeof(double2) + kTabMax * (2 * sizeof(double) + 4 * sizeof(int));
-static_assert(kSmem2 <= 232448, "group kernel shared memory exceeds the 227 KB per-CTA limit");
-static_assert(kP3First >= 0 && kP3First % 32 == 16, "pass 3 starts in the upper half of a warp (shuffle mask below)");
-static_assert(kGT % 32 == 0 && kGroups * kGT <= 1024, "groups are made of whole warps");
+static_assert(kP3First >= 16 && kP3First % 32 == 16, "pass 3 starts in the upper half of a warp");
+static_assert(kGT % 32 == 0, "groups are made of whole warps");
+
+// launch shape and shared-memory budget per grid size
+template <int NF>
+struct GC {
+    using D = Dim<NF>;
+    static constexpr bool F32 = NF == 1;                 // single-precision copies staged, grades on
+    static constexpr int Groups = NF == 1 ? kGGroups : 3;   // transforms in flight per CTA
+    static constexpr int N = D::N, Rows = D::Rows, Pairs = D::Pairs, Tile = 2 * D::N;
+    static constexpr uint32_t TileBytes = Tile * sizeof(double), TileBytes32 = Tile * sizeof(float);
+    static constexpr uint32_t StageBytes = 2 * TileBytes + (F32 ? 2 * TileBytes32 : 0);
+    static constexpr size_t StageDoubles = StageBytes / sizeof(double);
+    static constexpr bool Tabs = NF == 1;                // per-wavelength scalars staged in shared memory
+    static constexpr size_t Smem = 128 + (size_t)kGroupTw * sizeof(double2) + (size_t)kStages * StageBytes +
+                                   (size_t)Groups * kBuf * sizeof(double2) +
+                                   (Tabs ? kTabMax * (2 * sizeof(double) + 4 * sizeof(int)) : 0);
+    static_assert(Smem <= 232448, "group kernel shared memory exceeds the 227 KB per-CTA limit");
+    static_assert(Groups * kGT <= 1024, "too many threads");
+};
 
 // radix-R butterfly of a thread's R values, natural order in and out
 template <int R, class Z>
@@ -77,14 +89,14 @@ __device__ __forceinline__ void dft_any(Z* x) {
 }
 
 struct Rows2Params {
-    const double* D;       // [nplanes][kRows][N]
-    const double* T;       // [kRows][N]
-    const float* D32;
+    const double* D;       // [nplanes][Rows][N]
+    const double* T;       // [Rows][N]
+    const float* D32;      // single-precision copies (dim 1280)
     const float* T32;
-    double2* Y;            // [nplanes][nlam][kNC][kRows]
+    double2* Y;            // [nplanes][nlam][kNC][Rows]
     const GroupP3* p3;     // [nlam][2 kNC] pass-3 records per wavelength
-    const uint32_t* rows;  // [nlam][8] rows (k1, k2) pass 3 reads
-    const double* dmin;    // [nplanes][kRows]
+    const uint32_t* rows;  // [nlam][kGMaskStride] rows (k1, k2) pass 3 reads
+    const double* dmin;    // [nplanes][Rows]
     const double* csort;   // [nlam] descending
     const int* lorder;     // [nlam]
     const float2* tw32;    // [kG2][kG1 - 1] single-precision pass-1 twiddles (global memory, L1-resident)
@@ -112,15 +124,20 @@ struct TwMem32Pair {   // the float table, broadcast into both halves of a packe
 // FP64 for a double2 buffer, FP32 on one half (wavelength) of a packed-pair buffer.  The thread's record
 // is fetched (fetch_p3) while pass 2 runs: its L2 latency must not sit between the barriers.
 struct P3Reg {
-    double2 w;
+    double2 w, wc;
     float2 w32;
     int base, col;
 };
+template <int NF>
 __device__ __forceinline__ P3Reg fetch_p3(const GroupP3* __restrict__ tab) {
     const uint4* q = reinterpret_cast<const uint4*>(tab);
-    const uint4 a = __ldg(q), c = __ldg(q + 1);
+    const uint4 a = __ldg(q), c = __ldg(q + 2);
     P3Reg e;
     e.w = make_double2(__hiloint2double((int)a.y, (int)a.x), __hiloint2double((int)a.w, (int)a.z));
+    if (NF == 2) {
+        const uint4 m = __ldg(q + 1);
+        e.wc = make_double2(__hiloint2double((int)m.y, (int)m.x), __hiloint2double((int)m.w, (int)m.z));
+    }
     e.w32 = make_float2(__uint_as_float(c.x), __uint_as_float(c.y));
     e.base = (int)c.z;
     e.col = (int)c.w;
@@ -139,18 +156,12 @@ __device__ __forceinline__ double2 pass3(const double2* buf, const P3Reg& e, int
 }
 __device__ __forceinline__ double2 pass3(const Z2* buf, const P3Reg& e, int h) {
     float2 v[8];
-#if PSFR_G_LDS128
     const float4* r = reinterpret_cast<const float4*>(buf + e.base);   // (x.A, x.B, y.A, y.B) per element
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float4 q = r[i * kS2];
         v[i] = h ? make_float2(q.y, q.w) : make_float2(q.x, q.z);
     }
-#else
-    const float* r = reinterpret_cast<const float*>(buf + e.base) + h;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = make_float2(r[i * kS2 * 4], r[i * kS2 * 4 + 2]);
-#endif
     float2 a = v[7];
 #pragma unroll
     for (int i = 6; i >= 0; --i)
@@ -158,18 +169,14 @@ __device__ __forceinline__ double2 pass3(const Z2* buf, const P3Reg& e, int h) {
     return make_double2((double)a.x, (double)a.y);
 }
 
-// passes of one transform on the group's buffer, from the eight pass-1 inputs of every thread to the
-// store of the kept frequencies of both rows (see the file header for the index maps).  tabA / outA /
-// rowsA: pass-3 records, destination and needed-row masks of the transform (of half A of a packed
-// pair), tabB / outB / rowsB: of half B.
+// Passes 1 and 2 of one transform on the group's buffer, from the kG1 pass-1 inputs of every thread to
+// the rows pass 3 reads (see the file header for the index maps).  rowsA / rowsB: needed-row masks of the
+// transform (of the two halves of a packed pair).  Ends with the barrier that publishes pass 2.
 template <class Z, class TW>
-__device__ __forceinline__ void group_transform(Z (&x)[kG1], Z* buf, const TW& tw, int b, int grp,
-                                                const GroupP3* __restrict__ tabA, double2* __restrict__ outA,
-                                                const uint32_t* __restrict__ rowsA,
-                                                const GroupP3* __restrict__ tabB = nullptr, double2* __restrict__ outB = nullptr,
-                                                const uint32_t* __restrict__ rowsB = nullptr) {
+__device__ __forceinline__ void group_passes12(Z (&x)[kG1], Z* buf, const TW& tw, int b, int grp,
+                                               const uint32_t* __restrict__ rowsA, const uint32_t* __restrict__ rowsB) {
     dft_any<kG1>(x);
-    group_bar(grp);   // pass 3 of the previous unit is done with the buffer (its inputs were evaluated meanwhile)
+    group_bar(grp);   // pass 3 of the previous transform is done with the buffer (these inputs were evaluated meanwhile)
     {
         Z* dst = buf + (b & 7) * kS2 + (b >> 3);
         dst[0] = x[0];
@@ -198,39 +205,27 @@ __device__ __forceinline__ void group_transform(Z (&x)[kG1], Z* buf, const TW& t
         for (int i = 0; i < kG2; ++i) row[i] = z[i];
 #endif
     }
-    // the pass-3 threads fetch their records meanwhile
-    const bool p3 = b >= kP3First;
-    P3Reg ea, eb;
-    if (p3) {
-        ea = fetch_p3(tabA + (b - kP3First));
-        if (outB != nullptr) eb = fetch_p3(tabB + (b - kP3First));
-    }
-    group_bar(grp);
-    // ---- pass 3 (pruned): one needed output per thread; then the pair (X[k], X[-k]) on adjacent lanes
-    // untangles the two packed real rows; a packed pair does it once per wavelength (each has its own
-    // frequencies), reading its half.  Whole warps enter (the first pass-3 warp with its lower half idle)
-    // so that the shuffle has a compile-time full mask.
-    if (b >= kP3First - 16) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (h && outB == nullptr) break;   // a single transform, or a pair with only one wavelength
-            double2* o = h ? outB : outA;
-            double2 mine = make_double2(0.0, 0.0);
-            if (p3) mine = pass3(buf, h ? eb : ea, h);
-            double2 other;
-            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-            other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-            if (p3 && !(b & 1)) {
-                const double2 za = mine, zb = other;
-                st_global_256(o + (size_t)(h ? eb.col : ea.col) * kRows, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
-                              make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
-            }
-        }
+}
+
+// the pair (X[k], X[-k]) on adjacent lanes untangles the two packed real rows: one 32-byte store per
+// kept frequency.  Whole warps enter so that the shuffle has a compile-time full mask.
+__device__ __forceinline__ void untangle_store(double2 mine, bool active, int b, double2* dst) {
+    double2 other;
+    other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+    other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+    if (active && !(b & 1)) {
+        const double2 za = mine, zb = other;
+        st_global_256(dst, make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y)),
+                      make_double2(0.5 * (za.y + zb.y), 0.5 * (zb.x - za.x)));
     }
 }
 
-__global__ void __launch_bounds__(kGroups* kGT, 1)
+template <int NF>
+__global__ void __launch_bounds__(GC<NF>::Groups* kGT, 1)
 group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
+    using C = GC<NF>;
+    constexpr int kGroups = C::Groups, kN = C::N, kRows = C::Rows, kPairs = C::Pairs, kTile = C::Tile;
+    constexpr size_t kStageDoubles = C::StageDoubles;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     int* released = reinterpret_cast<int*>(full + kStages);
@@ -241,7 +236,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     double2* tw1 = reinterpret_cast<double2*>(smem_raw + 128);   // [kG2][kG1 - 1] pass-1 twiddles w_160^(n2 k1)
     double* ring = reinterpret_cast<double*>(tw1 + kGroupTw);
     double2* bufs = reinterpret_cast<double2*>(ring + (size_t)kStages * kStageDoubles);
-    double* tab_c = reinterpret_cast<double*>(bufs + (size_t)kGroups * kBuf);
+    double* tab_c = reinterpret_cast<double*>(bufs + (size_t)kGroups * kBuf);   // C::Tabs only
     double* tab_rc = tab_c + kTabMax;
     int* tab_lo = reinterpret_cast<int*>(tab_rc + kTabMax);
     int* tab_cut = tab_lo + kTabMax;      // per sorted wavelength: float bit patterns of cut / c, grade / c
@@ -250,7 +245,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
     const int grp = threadIdx.x / kGT, b = threadIdx.x % kGT;
     double2* buf = bufs + (size_t)grp * kBuf;
     const int items = p.nplanes * kPairs;
-    const bool tabbed = p.nlam <= kTabMax;
+    const bool tabbed = C::Tabs && p.nlam <= kTabMax;
     auto c_of = [&](int pos) { return tabbed ? tab_c[pos] : __ldg(p.csort + pos); };
 
     auto issue = [&](int s) {
@@ -269,7 +264,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
             la_of[s] = lo;
             const int la = lo;
             hi = p.nlam;
-            while (lo < hi) {
+            while (C::F32 && lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (c_of(mid) * dm >= p.f32_min) lo = mid + 1; else hi = mid;
             }
@@ -280,12 +275,14 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 return;
             }
             const size_t off = ((size_t)plane * kRows + 2 * rp) * kN, offT = (size_t)(2 * rp) * kN;
-            mbar_expect_tx(full + s, kStageBytes);
-            tma_load_1d(dst, p.D + off, kTileBytes, full + s);
-            tma_load_1d(dst + kTile, p.T + offT, kTileBytes, full + s);
-            float* dst32 = reinterpret_cast<float*>(dst + 2 * kTile);
-            tma_load_1d(dst32, p.D32 + off, kTileBytes32, full + s);
-            tma_load_1d(dst32 + kTile, p.T32 + offT, kTileBytes32, full + s);
+            mbar_expect_tx(full + s, C::StageBytes);
+            tma_load_1d(dst, p.D + off, C::TileBytes, full + s);
+            tma_load_1d(dst + kTile, p.T + offT, C::TileBytes, full + s);
+            if (C::F32) {
+                float* dst32 = reinterpret_cast<float*>(dst + 2 * kTile);
+                tma_load_1d(dst32, p.D32 + off, C::TileBytes32, full + s);
+                tma_load_1d(dst32 + kTile, p.T32 + offT, C::TileBytes32, full + s);
+            }
         } else {
             item_of[s] = -1;
             mbar_arrive(full + s);
@@ -294,7 +291,6 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
 
     for (int i = threadIdx.x; i < kGroupTw; i += blockDim.x) tw1[i] = g_tw[i];
     const TwSmem twr{tw1 + (b >> 3) * (kG1 - 1)};
-    const TwMem32Pair twp{p.tw32 + (b >> 3) * (kG1 - 1)};
     if (tabbed)
         for (int i = threadIdx.x; i < p.nlam; i += blockDim.x) {
             const double cv = __ldg(p.csort + i);
@@ -360,6 +356,7 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         }
     };
 
+    const bool p3 = b >= kP3First, p3warp = b >= kP3First - 16;
 #pragma unroll 1
     for (;;) {
         int rel = base + grp;
@@ -372,94 +369,148 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         const int slot = (cur & 1) ? ns_of[s] - 1 - rel : rel;
         const double* sD = ring + (size_t)s * kStageDoubles;
         const double* sT = sD + kTile;
-        const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);
-        const float* sT32 = sD32 + kTile;
         const int plane = item / kPairs, rp = item % kPairs;
         auto lam_of = [&](int pos) { return tabbed ? tab_lo[pos] : __ldg(p.lorder + pos); };
         auto out_of = [&](int lam) { return p.Y + ((size_t)plane * p.nlam + lam) * kNC * kRows + 2 * rp; };
-        auto n2f_of = [&](int pos) {
-            return tabbed ? __int_as_float(tab_n2f[pos]) : (float)(-c_of(pos) * 1.44269504088896338700);
-        };
-        auto cut_of = [&](int pos) {
-            return tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut / c_of(pos)));
-        };
-        if (slot < npair) {
-            // ---- single-precision pair (every entry below exp(-f32_min) of the OTF peak at both
-            // wavelengths): inputs, transform and buffer in FP32, the two wavelengths as the two halves
-            // of one packed transform (Z2: FADD2 / FMUL2 / FFMA2)
-            const int posA = la + 2 * slot;
-            const bool two = posA + 1 < lb;
-            const int posB = two ? posA + 1 : posA;
-            const int lamA = lam_of(posA), lamB = lam_of(posB);
-            const float nA = n2f_of(posA), nB = n2f_of(posB);
-            const int cut32 = cut_of(posB);   // c_B <= c_A: an entry below the cut at B is below it at A
-            Z2 x[kG1];
+        if constexpr (C::F32) {
+            const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);
+            const float* sT32 = sD32 + kTile;
+            auto n2f_of = [&](int pos) {
+                return tabbed ? __int_as_float(tab_n2f[pos]) : (float)(-c_of(pos) * 1.44269504088896338700);
+            };
+            auto cut_of = [&](int pos) { return tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut / c_of(pos))); };
+            if (slot < npair) {
+                // ---- single-precision pair (every entry below exp(-f32_min) of the OTF peak at both
+                // wavelengths): inputs, transform and buffer in FP32, the two wavelengths as the two halves
+                // of one packed transform (Z2: FADD2 / FMUL2 / FFMA2)
+                const int posA = la + 2 * slot;
+                const bool two = posA + 1 < lb;
+                const int posB = two ? posA + 1 : posA;
+                const int lamA = lam_of(posA), lamB = lam_of(posB);
+                const float nA = n2f_of(posA), nB = n2f_of(posB);
+                const int cut32 = cut_of(posB);   // c_B <= c_A: an entry below the cut at B is below it at A
+                const TwMem32Pair twp{p.tw32 + (b >> 3) * (kG1 - 1)};
+                Z2 x[kG1];
 #pragma unroll
-            for (int n1 = 0; n1 < kG1; ++n1) {
-                const int n = n1 * kGT + b;
-                const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
-                const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
-                if (__all_sync(0xffffffffu, dead)) {
-                    x[n1].x = F2(0.f, 0.f);
-                    x[n1].y = F2(0.f, 0.f);
-                } else {
-                    x[n1].x = F2(ex2_approx(nA * d0) * t0, ex2_approx(nB * d0) * t0);
-                    x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
+                for (int n1 = 0; n1 < kG1; ++n1) {
+                    const int n = n1 * kGT + b;
+                    const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
+                    const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
+                    if (__all_sync(0xffffffffu, dead)) {
+                        x[n1].x = F2(0.f, 0.f);
+                        x[n1].y = F2(0.f, 0.f);
+                    } else {
+                        x[n1].x = F2(ex2_approx(nA * d0) * t0, ex2_approx(nB * d0) * t0);
+                        x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
+                    }
                 }
-            }
-            group_transform(x, reinterpret_cast<Z2*>(buf), twp, b, grp, p.p3 + (size_t)lamA * 2 * kNC, out_of(lamA),
-                            p.rows + lamA * kGMaskStride, p.p3 + (size_t)lamB * 2 * kNC, two ? out_of(lamB) : nullptr,
-                            p.rows + lamB * kGMaskStride);
-        } else {
-            // ---- FP64 unit; the exp is graded per 32-cell segment of both rows
-            const int pos = lb + (slot - npair);
-            const int lam = lam_of(pos);
-            const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
-            const double negc = -cl;
-            const float negc2f = n2f_of(pos);
-            const int cut32 = cut_of(pos);
-            const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
-            double2 x[kG1];
-#pragma unroll
-            for (int n1 = 0; n1 < kG1; ++n1) {
-                const int n = n1 * kGT + b;
-                const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
-                const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
-                const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
-                const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
-                const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
-                if (__all_sync(0xffffffffu, dead)) {
-                    x[n1] = make_double2(0.0, 0.0);
-                } else if (__all_sync(0xffffffffu, cheap)) {
-                    x[n1] = make_double2(f2d_bits(ex2_approx(negc2f * d0) * t0), f2d_bits(ex2_approx(negc2f * d1) * t1));
-                } else {
-                    x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+                Z2* zbuf = reinterpret_cast<Z2*>(buf);
+                group_passes12(x, zbuf, twp, b, grp, p.rows + lamA * kGMaskStride, p.rows + lamB * kGMaskStride);
+                // the pass-3 threads fetch their records while pass 2 runs
+                P3Reg ea, eb;
+                ea.col = eb.col = 0;
+                if (p3) {
+                    ea = fetch_p3<1>(p.p3 + (size_t)lamA * 2 * kNC + (b - kP3First));
+                    eb = fetch_p3<1>(p.p3 + (size_t)lamB * 2 * kNC + (b - kP3First));
                 }
+                group_bar(grp);
+                if (p3warp) {
+                    untangle_store(p3 ? pass3(zbuf, ea, 0) : make_double2(0.0, 0.0), p3, b, out_of(lamA) + (size_t)ea.col * kRows);
+                    if (two)
+                        untangle_store(p3 ? pass3(zbuf, eb, 1) : make_double2(0.0, 0.0), p3, b,
+                                       out_of(lamB) + (size_t)eb.col * kRows);
+                }
+                base += kGroups;
+                continue;
             }
-            group_transform(x, buf, twr, b, grp, p.p3 + (size_t)lam * 2 * kNC, out_of(lam), p.rows + lam * kGMaskStride);
         }
+        // ---- FP64 unit; dim 1280: the exp is graded per 32-cell segment of both rows; dim 2560: two
+        // interleaved sub-transforms, pass 3 combines them
+        const int pos = lb + (slot - npair);
+        const int lam = lam_of(pos);
+        const double cl = c_of(pos), rcl = tabbed ? tab_rc[pos] : 1.0 / cl;
+        const double negc = -cl;
+        const uint32_t* need = p.rows + lam * kGMaskStride;
+        P3Reg e;
+        e.col = 0;
+        double2 f0 = make_double2(0.0, 0.0), mine = make_double2(0.0, 0.0);
+#pragma unroll 1
+        for (int sub = 0; sub < NF; ++sub) {
+            double2 x[kG1];
+            if constexpr (C::F32) {
+                const float* sD32 = reinterpret_cast<const float*>(sD + 2 * kTile);
+                const float* sT32 = sD32 + kTile;
+                const float negc2f = tabbed ? __int_as_float(tab_n2f[pos]) : (float)(negc * 1.44269504088896338700);
+                const int cut32 = tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut * rcl));
+                const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
+#pragma unroll
+                for (int n1 = 0; n1 < kG1; ++n1) {
+                    const int n = n1 * kGT + b;
+                    const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
+                    const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
+                    const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
+                    const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
+                    const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
+                    if (__all_sync(0xffffffffu, dead)) {
+                        x[n1] = make_double2(0.0, 0.0);
+                    } else if (__all_sync(0xffffffffu, cheap)) {
+                        x[n1] = make_double2(f2d_bits(ex2_approx(negc2f * d0) * t0), f2d_bits(ex2_approx(negc2f * d1) * t1));
+                    } else {
+                        x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+                    }
+                }
+            } else {
+                // cut threshold on D itself, tested on the integer pipe (a non-negative double orders like
+                // its high word; the signed compare keeps a D rounded slightly below zero alive)
+                const int cut_hi = __double2hiint(p.cut * rcl);
+#pragma unroll
+                for (int n1 = 0; n1 < kG1; ++n1) {
+                    const int n = NF * (n1 * kGT + b) + sub;
+                    const double d0 = sD[n], d1 = sD[kN + n], t0 = sT[n], t1 = sT[kN + n];
+                    const bool dead = (is_zero_bits(t0) | (__double2hiint(d0) >= cut_hi)) &
+                                      (is_zero_bits(t1) | (__double2hiint(d1) >= cut_hi));
+                    if (__all_sync(0xffffffffu, dead)) x[n1] = make_double2(0.0, 0.0);
+                    else x[n1] = make_double2(fast_exp(negc * d0) * t0, fast_exp(negc * d1) * t1);
+                }
+            }
+            group_passes12(x, buf, twr, b, grp, need, nullptr);
+            if (sub == 0 && p3) e = fetch_p3<NF>(p.p3 + (size_t)lam * 2 * kNC + (b - kP3First));
+            group_bar(grp);
+            if (p3) {
+                const double2 a = pass3(buf, e, 0);
+                if (NF == 1) mine = a;
+                else if (sub == 0) f0 = a;
+                else mine = cadd(f0, cmul(a, e.wc));   // X[k] = F0[k mod 1280] + w_N^k F1[k mod 1280]
+            }
+        }
+        if (p3warp) untangle_store(mine, p3, b, out_of(lam) + (size_t)e.col * kRows);
         base += kGroups;
     }
 }
 
 }  // namespace
 
-int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
-    if (c->NF != 1) return set_error(c, PSFR_E_UNSUPPORTED, "the group row kernel is dim-1280 only");
-    if (int rc = ensure_dynamic_smem(c, group_rows_kernel, kSmem2)) return rc;
+template <int NF>
+static int group_rows_t(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
+    using C = GC<NF>;
+    if (int rc = ensure_dynamic_smem(c, group_rows_kernel<NF>, C::Smem)) return rc;
     Rows2Params p{c->d_dphi, c->d_otf, c->d_dphi32, c->d_otf32, c->d_ybuf, c->d_p3, c->d_p2mask, c->d_dmin, c->d_csort,
                   c->d_lorder, c->d_twg32, c->d_counter, c->exp_cut, c->exp_grade, c->f32_rows, nplanes, nlam};
     int grid = c->sm_count;
-    if (grid > nplanes * kPairs) grid = nplanes * kPairs;
+    if (grid > nplanes * C::Pairs) grid = nplanes * C::Pairs;
     PSFR_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), s));
     int rc = hot_event(c, 0, s);
     if (rc) return rc;
-    group_rows_kernel<<<grid, kGroups * kGT, kSmem2, s>>>(p, c->d_twg);
+    group_rows_kernel<NF><<<grid, C::Groups * kGT, C::Smem, s>>>(p, c->d_twg);
     PSFR_LAUNCH_CHECK(c);
     if ((rc = hot_event(c, 1, s))) return rc;
     c->hot_launches += 1;
     c->hot_psfs += (long long)nplanes * nlam;
     return PSFR_OK;
+}
+
+int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s) {
+    return c->NF == 1 ? group_rows_t<1>(c, nplanes, nlam, s) : group_rows_t<2>(c, nplanes, nlam, s);
 }
 
 }  // namespace psfr

@@ -28,7 +28,7 @@ struct Dim {
 // Index maps: n = n1*kGThreads + n2*8 + n3,  k = k1 + kG1*k2 + 160*k3.
 // Tables: pass-1 twiddles w_160^(n2 k1) [kG2][kG1 - 1], and per wavelength
 //  * the record of the pruned third pass for thread t: output k (a kept frequency or its mirror), as the
-//    Horner base w = w_N^k in FP64 and FP32, the offset of its row k1*kGS1 + k2 in the transform buffer and
+//    Horner base w = w_1280^k in FP64 and FP32, the offset of its row k1*kGS1 + k2 in the transform buffer and
 //    the kept frequency (column of Y) the pair (t, t xor 1) = (X[k], X[-k]) belongs to;
 //  * the rows (k1, k2) pass 3 reads, as one kG2-bit mask per k1: pass 2 stores only those.
 #ifndef PSFR_G_GEOM
@@ -46,12 +46,13 @@ constexpr int kGroupTw = kG2 * (kG1 - 1);
 constexpr int kGMaskStride = 16;         // uint32 masks per wavelength (kG1 used)
 static_assert(kG1 * kG2 * 8 == kNB && kG1 <= kGMaskStride, "group geometry");
 struct alignas(16) GroupP3 {
-    double2 w;
+    double2 w;       // w_1280^(k mod 1280): Horner base of the 1280-point (sub-)transform
+    double2 wc;      // w_N^k: combine twiddle of the two interleaved sub-transforms (dim 2560)
     float2 w32;
     uint32_t base;
     uint32_t col;
 };
-static_assert(sizeof(GroupP3) == 32, "GroupP3 is loaded as two 16-byte words");
+static_assert(sizeof(GroupP3) == 48, "GroupP3 is loaded as three 16-byte words");
 constexpr int kAO = PSFR_AO_DIM;        // 80
 constexpr int kPSF = PSFR_PSF_DIM;      // 40
 constexpr int kNS = 2 * kPSF;           // 80 sampled rows / columns per PSF
@@ -103,7 +104,7 @@ struct Ctx {
     float* d_dphi32 = nullptr;   // [max_planes][rows][N] single-precision copy of d_dphi (dim 1280: block grading + FP32 row pairs)
     float* d_otf32 = nullptr;    // [rows][N] single-precision copy of d_otf
     float2* d_tw32 = nullptr;    // twiddles of d_tw rounded to single precision
-    double2* d_twg = nullptr;    // [kGroupTw] pass-1 twiddles of the group row kernel (dim 1280)
+    double2* d_twg = nullptr;    // [kGroupTw] pass-1 twiddles of the group row kernel
     float2* d_twg32 = nullptr;   // the same in single precision
     GroupP3* d_p3 = nullptr;     // [max_lambda][2 kNC] pass-3 records of the group row kernel
     uint32_t* d_p2mask = nullptr; // [max_lambda][8] rows (k1, k2) that pass 3 reads
@@ -113,7 +114,7 @@ struct Ctx {
     double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
     double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
     double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
-    int row_kernel = 2;          // dim 1280: 2 group_rows_kernel (psfr_hot2.cu), 1 hot_rows_kernel (PSFR_OPT_ROW_KERNEL)
+    int row_kernel = 2;          // 2 group_rows_kernel (psfr_hot2.cu), 1 hot_rows_kernel (PSFR_OPT_ROW_KERNEL)
     double2* d_ybuf = nullptr;   // [max_planes*max_lambda][kNC][rows] pruned row-pass output
     double2* d_wsamp = nullptr;  // [max_lambda][2][kNS] combine twiddles of the sampled outputs / mirrors (NF = 2)
     double2* d_wcol = nullptr;   // [max_lambda][2][kNC] the same for the kept row-pass frequencies (NF = 2)
@@ -219,7 +220,7 @@ int run_debug_exp(Ctx* c, const double* x_dev, double* y_dev, int n, cudaStream_
 // row pass with fused exp(-c D) * OTF for nplanes x nlam, then pruned column pass summing
 // the ndir planes of each draw into d_samp [ndraw*nlam][80][80]
 int run_pruned_psf(Ctx* c, int ndraw, int ndir, int nlam, cudaStream_t s);
-// psfr_hot2.cu: the dim-1280 row pass (one transform per 160-thread group, data in shared memory)
+// psfr_hot2.cu: the row pass by groups of threads (one transform per 128-thread group, data in shared memory)
 int run_group_rows(Ctx* c, int nplanes, int nlam, cudaStream_t s);
 
 // ---- psfr_psd.cu ---------------------------------------------------------------------

@@ -326,8 +326,8 @@ def test_graded_precision_is_invisible(psfrec, seeing, L0, GL):
 
 
 def test_row_kernels_agree(psfrec, psd1):
-    """The two row kernels of dim 1280 - PSFR_OPT_ROW_KERNEL = 2 (default, csrc/psfr_hot2.cu: one
-    160-thread group per row transform, data in shared memory) and 1 (csrc/psfr_hot.cu: one warp per
+    """The two row kernels - PSFR_OPT_ROW_KERNEL = 2 (default, csrc/psfr_hot2.cu: one 128-thread group per
+    row transform, data in shared memory, pruned third pass) and 1 (csrc/psfr_hot.cu: one warp per
     transform, data in registers) - must give the same planes."""
     from muse_psfr_b200 import _lib
     ctx = psfrec.get_context()
@@ -345,6 +345,25 @@ def test_row_kernels_agree(psfrec, psd1):
         for k in range(2):
             assert_image_close(got[k], want[k])
             assert_image_close(ref[k], want[k])
+
+def test_config5_row_kernels_agree(psfrec, psd5, golden):
+    """dim 2560: the group row kernel (two interleaved 1280-point sub-transforms combined in pass 3) against
+    the warp row kernel and the reference fixture."""
+    from muse_psfr_b200 import _lib
+    g = golden('ref_config5')
+    lam = np.concatenate([g['lbda'], np.linspace(490, 930, 100)[[0, 37, 99]]])
+    ctx = psfrec.get_context(dim=2560)
+    got2 = psfrec.psf_muse(psd5[0], lam)
+    try:
+        ctx.set_option(_lib.OPT_ROW_KERNEL, 1)
+        got1 = psfrec.psf_muse(psd5[0], lam)
+    finally:
+        ctx.set_option(_lib.OPT_ROW_KERNEL, 2)
+    assert np.isfinite(got2).all()
+    assert rel_to_peak(got2, got1) < 1e-13
+    for k in range(len(g['lbda'])):
+        assert_image_close(got2[k], g['psf_muse'][k])
+
 
 def test_wavelength_below_grid_limit(psfrec, psd1):
     with pytest.raises(ValueError):
