@@ -390,18 +390,35 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 const float nA = n2f_of(posA), nB = n2f_of(posB);
                 const int cut32 = cut_of(posB);   // c_B <= c_A: an entry below the cut at B is below it at A
                 const TwMem32Pair twp{p.tw32 + (b >> 3) * (kG1 - 1)};
+                // The inputs are fetched and classified in two batches of kG1 / 2 cells: all loads of a batch
+                // are in flight together and ONE warp reduction (REDUX.AND on the packed per-cell bits) replaces
+                // a vote + branch per cell, whose latencies used to add up cell after cell.
                 Z2 x[kG1];
 #pragma unroll
-                for (int n1 = 0; n1 < kG1; ++n1) {
-                    const int n = n1 * kGT + b;
-                    const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
-                    const bool dead = ((t0 == 0.f) | (__float_as_int(d0) >= cut32)) & ((t1 == 0.f) | (__float_as_int(d1) >= cut32));
-                    if (__all_sync(0xffffffffu, dead)) {
-                        x[n1].x = F2(0.f, 0.f);
-                        x[n1].y = F2(0.f, 0.f);
-                    } else {
-                        x[n1].x = F2(ex2_approx(nA * d0) * t0, ex2_approx(nB * d0) * t0);
-                        x[n1].y = F2(ex2_approx(nA * d1) * t1, ex2_approx(nB * d1) * t1);
+                for (int hb = 0; hb < kG1; hb += kG1 / 2) {
+                    float d0[kG1 / 2], d1[kG1 / 2], t0[kG1 / 2], t1[kG1 / 2];
+                    unsigned bits = 0;
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        const int n = (hb + j) * kGT + b;
+                        d0[j] = sD32[n];
+                        d1[j] = sD32[kN + n];
+                        t0[j] = sT32[n];
+                        t1[j] = sT32[kN + n];
+                        const bool dead = ((t0[j] == 0.f) | (__float_as_int(d0[j]) >= cut32)) &
+                                          ((t1[j] == 0.f) | (__float_as_int(d1[j]) >= cut32));
+                        bits |= (unsigned)dead << j;
+                    }
+                    const unsigned all = __reduce_and_sync(0xffffffffu, bits);
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        if ((all >> j) & 1) {
+                            x[hb + j].x = F2(0.f, 0.f);
+                            x[hb + j].y = F2(0.f, 0.f);
+                        } else {
+                            x[hb + j].x = F2(ex2_approx(nA * d0[j]) * t0[j], ex2_approx(nB * d0[j]) * t0[j]);
+                            x[hb + j].y = F2(ex2_approx(nA * d1[j]) * t1[j], ex2_approx(nB * d1[j]) * t1[j]);
+                        }
                     }
                 }
                 Z2* zbuf = reinterpret_cast<Z2*>(buf);
@@ -444,19 +461,34 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 const int cut32 = tabbed ? tab_cut[pos] : __float_as_int((float)(p.cut * rcl));
                 const int grade32 = tabbed ? tab_grade[pos] : __float_as_int((float)(p.grade * rcl));
 #pragma unroll
-                for (int n1 = 0; n1 < kG1; ++n1) {
-                    const int n = n1 * kGT + b;
-                    const float d0 = sD32[n], d1 = sD32[kN + n], t0 = sT32[n], t1 = sT32[kN + n];
-                    const bool z0 = t0 == 0.f, z1 = t1 == 0.f;
-                    const int h0 = __float_as_int(d0), h1 = __float_as_int(d1);
-                    const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
-                    const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
-                    if (__all_sync(0xffffffffu, dead)) {
-                        x[n1] = make_double2(0.0, 0.0);
-                    } else if (__all_sync(0xffffffffu, cheap)) {
-                        x[n1] = make_double2(f2d_bits(ex2_approx(negc2f * d0) * t0), f2d_bits(ex2_approx(negc2f * d1) * t1));
-                    } else {
-                        x[n1] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+                for (int hb = 0; hb < kG1; hb += kG1 / 2) {   // two batches, one warp reduction each (see the pair path)
+                    float d0[kG1 / 2], d1[kG1 / 2], t0[kG1 / 2], t1[kG1 / 2];
+                    unsigned bits = 0;
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        const int n = (hb + j) * kGT + b;
+                        d0[j] = sD32[n];
+                        d1[j] = sD32[kN + n];
+                        t0[j] = sT32[n];
+                        t1[j] = sT32[kN + n];
+                        const bool z0 = t0[j] == 0.f, z1 = t1[j] == 0.f;
+                        const int h0 = __float_as_int(d0[j]), h1 = __float_as_int(d1[j]);
+                        const bool dead = (z0 | (h0 >= cut32)) & (z1 | (h1 >= cut32));
+                        const bool cheap = (z0 | (h0 >= grade32)) & (z1 | (h1 >= grade32));
+                        bits |= ((unsigned)dead << j) | ((unsigned)cheap << (8 + j));
+                    }
+                    const unsigned all = __reduce_and_sync(0xffffffffu, bits);
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        const int n = (hb + j) * kGT + b;
+                        if ((all >> j) & 1) {
+                            x[hb + j] = make_double2(0.0, 0.0);
+                        } else if ((all >> (8 + j)) & 1) {
+                            x[hb + j] = make_double2(f2d_bits(ex2_approx(negc2f * d0[j]) * t0[j]),
+                                                     f2d_bits(ex2_approx(negc2f * d1[j]) * t1[j]));
+                        } else {
+                            x[hb + j] = make_double2(fast_exp(negc * sD[n]) * sT[n], fast_exp(negc * sD[kN + n]) * sT[kN + n]);
+                        }
                     }
                 }
             } else {
@@ -464,13 +496,26 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                 // its high word; the signed compare keeps a D rounded slightly below zero alive)
                 const int cut_hi = __double2hiint(p.cut * rcl);
 #pragma unroll
-                for (int n1 = 0; n1 < kG1; ++n1) {
-                    const int n = NF * (n1 * kGT + b) + sub;
-                    const double d0 = sD[n], d1 = sD[kN + n], t0 = sT[n], t1 = sT[kN + n];
-                    const bool dead = (is_zero_bits(t0) | (__double2hiint(d0) >= cut_hi)) &
-                                      (is_zero_bits(t1) | (__double2hiint(d1) >= cut_hi));
-                    if (__all_sync(0xffffffffu, dead)) x[n1] = make_double2(0.0, 0.0);
-                    else x[n1] = make_double2(fast_exp(negc * d0) * t0, fast_exp(negc * d1) * t1);
+                for (int hb = 0; hb < kG1; hb += kG1 / 2) {
+                    double d0[kG1 / 2], d1[kG1 / 2], t0[kG1 / 2], t1[kG1 / 2];
+                    unsigned bits = 0;
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        const int n = NF * ((hb + j) * kGT + b) + sub;
+                        d0[j] = sD[n];
+                        d1[j] = sD[kN + n];
+                        t0[j] = sT[n];
+                        t1[j] = sT[kN + n];
+                        const bool dead = (is_zero_bits(t0[j]) | (__double2hiint(d0[j]) >= cut_hi)) &
+                                          (is_zero_bits(t1[j]) | (__double2hiint(d1[j]) >= cut_hi));
+                        bits |= (unsigned)dead << j;
+                    }
+                    const unsigned all = __reduce_and_sync(0xffffffffu, bits);
+#pragma unroll
+                    for (int j = 0; j < kG1 / 2; ++j) {
+                        if ((all >> j) & 1) x[hb + j] = make_double2(0.0, 0.0);
+                        else x[hb + j] = make_double2(fast_exp(negc * d0[j]) * t0[j], fast_exp(negc * d1[j]) * t1[j]);
+                    }
                 }
             }
             group_passes12(x, buf, twr, b, grp, need, nullptr);
