@@ -160,12 +160,16 @@ PSFR_API int psfr_mean_refit(psfr_ctx* ctx, int ncube, int nlam, const double* c
 PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* lambda_nm, int deg,
                  const double* y, double* coef, void* stream);
 
-/* Options.  PSFR_OPT_EXP_CUT (default 64): in the pruned stage-B row pass (psfr_psf_cube,
+/* Options.  PSFR_OPT_EXP_CUT (default 45): in the pruned stage-B row pass (psfr_psf_cube,
  * psfr_compute_batch) entries of exp(-Dphi/2) smaller than exp(-cut) are flushed to zero and
- * row pairs that are below the cut everywhere are not transformed.  The OTF peak is 1, so
- * the default drops terms below 1.6e-28 of it - twelve orders of magnitude under the FP64
- * rounding of the transform itself.  A value >= 745 (exp underflows) disables the cut.
- * psfr_psd_to_psf (full-grid parity mode) never applies it (nor the grades below).
+ * row pairs that are below the cut everywhere are not transformed.  The OTF peak is 1, so the
+ * default drops terms below 2.9e-20 of it - four orders of magnitude under the FP64 rounding of a
+ * single kept term; beyond the cut radius exp(-Dphi/2) falls off faster than exponentially, so even
+ * a coherent sum of everything dropped stays below ~1e-15 of the OTF peak, against a PSF peak of
+ * 15 (2 arcsec seeing) to several 1000.  tools/parity_sweep.py holds the default against the oracle
+ * over the BASELINE configs and the corners of the config-4 sweep (profiles/).  A value >= 745 (exp
+ * underflows) disables the cut; psfr_psd_to_psf (full-grid parity mode) never applies it (nor the
+ * grades below).
  *
  * Graded precision of the same pass (the OTF peak is exactly 1, so an entry's size bounds
  * what an error in it can do to the result):

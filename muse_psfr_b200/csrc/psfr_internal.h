@@ -111,7 +111,7 @@ struct Ctx {
     double* d_csort = nullptr;   // [max_lambda] c_lambda in descending order (unit classes of the row kernel)
     int* d_lorder = nullptr;     // [max_lambda] wavelength index of sorted position i
     int* d_counter = nullptr;    // work counter of the persistent stage-B row kernel
-    double exp_cut = 64.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
+    double exp_cut = 45.0;       // OTF entries below exp(-exp_cut) are flushed to zero (PSFR_OPT_EXP_CUT)
     double exp_grade = 20.0;     // blocks entirely below exp(-exp_grade) use the single-precision exp (PSFR_OPT_EXP_GRADE)
     double f32_rows = 25.0;      // row pairs entirely below exp(-f32_rows) run in single precision (PSFR_OPT_F32_ROWS)
     int row_kernel = 2;          // 2 group_rows_kernel (psfr_hot2.cu), 1 hot_rows_kernel (PSFR_OPT_ROW_KERNEL)

@@ -273,19 +273,21 @@ def test_psf_muse_pruned_equals_full_grid(psfrec, psd1):
 
 
 def test_underflow_cut_is_invisible(psfrec):
-    """Bad seeing: most of exp(-Dphi/2) is < e^-64 and the row kernel flushes those entries
-    (and whole row pairs) to zero.  The result must equal the un-cut evaluation to FP64
-    rounding and the oracle to the PSF tolerance."""
+    """Bad seeing: most of exp(-Dphi/2) is below the underflow cut (default e^-45) and the row kernel
+    flushes those entries (and whole row pairs) to zero.  The result must equal the un-cut evaluation
+    to FP64 rounding and the oracle to the PSF tolerance."""
     from muse_psfr_b200 import _lib
     psd = orc.simul_psd_wfm([0.36, 0.64], (100, 10000), 1.68, 19.9)
     lam = np.array([490., 640., 930.])
     ref = orc.psf_muse(psd, lam)
     ctx = psfrec.get_context()
+    default_cut = ctx.info()['exp_cut']
     try:
         ctx.set_option(_lib.OPT_EXP_CUT, 1000.0)        # cut disabled
         full = psfrec.psf_muse(psd, lam)
     finally:
-        ctx.set_option(_lib.OPT_EXP_CUT, 64.0)
+        ctx.set_option(_lib.OPT_EXP_CUT, default_cut)
+    assert ctx.info()['exp_cut'] == default_cut == 45.0
     cut = psfrec.psf_muse(psd, lam)
     # structure-function rows far from the centre exceed the cut at 490 nm: the skip really ran
     d = ctx.get_structure_function(0)

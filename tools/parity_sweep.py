@@ -1,5 +1,6 @@
-"""Hardware parity sweep of the pruned stage-B path (underflow cut + graded precision, and the same
-with both grades off) against the CPU oracle, over the BASELINE configs at their stated sizes.
+"""Hardware parity sweep of the pruned stage-B path (underflow cut + graded precision; the same with
+both grades off; and with the cut off as well) against the CPU oracle, over the BASELINE configs at
+their stated sizes.
 
     python tools/parity_sweep.py [--out gpurun_out/parity_sweep.json] [--draws 64] [--configs 4,2,3,5]
 
@@ -26,7 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 
 LBDA35 = np.linspace(490, 930, 35)
 FLOOR = 1e-6
-OPTION_SETS = {'default': {}, 'allfp64': {'grade': 1e30, 'f32_rows': 1e30}}
+OPTION_SETS = {'default': {}, 'allfp64': {'grade': 1e30, 'f32_rows': 1e30},
+               'allfp64_nocut': {'grade': 1e30, 'f32_rows': 1e30, 'exp_cut': 1000.0}}
 
 
 def config4_draws(n, corners=True):
@@ -79,6 +81,7 @@ def set_options(ctx, opts):
     info = ctx.info()
     ctx.set_option(_lib.OPT_EXP_GRADE, opts.get('grade', info['exp_grade']))
     ctx.set_option(_lib.OPT_F32_ROWS, opts.get('f32_rows', info['f32_rows']))
+    ctx.set_option(_lib.OPT_EXP_CUT, opts.get('exp_cut', info['exp_cut']))
     return info
 
 
@@ -86,6 +89,7 @@ def restore_options(ctx, info):
     from muse_psfr_b200 import _lib
     ctx.set_option(_lib.OPT_EXP_GRADE, info['exp_grade'])
     ctx.set_option(_lib.OPT_F32_ROWS, info['f32_rows'])
+    ctx.set_option(_lib.OPT_EXP_CUT, info['exp_cut'])
 
 
 def gpu_batch(psfrec, opts, lbda, seeing, GL, L0, dim=1280, **kw):
