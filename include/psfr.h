@@ -176,7 +176,7 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  * PSFR_OPT_EXP_GRADE (default 20): a segment of 2 x 32 OTF entries whose every live entry is
  * below exp(-grade) = 2.1e-9 evaluates exp on the special-function unit in single precision
  * (relative error ~4e-6, i.e. < 1e-14 of the peak per entry); other blocks use the FP64 exp.
- * PSFR_OPT_F32_ROWS (default 25, dim 1280 only): a row pair whose every entry is below
+ * PSFR_OPT_F32_ROWS (default 25, dim 1280 only; dim 2560 runs every unit in FP64): a row pair whose every entry is below
  * exp(-thr) = 1.4e-11 is evaluated AND transformed in single precision; all other rows and
  * the whole column pass are FP64.
  * Measured against the all-FP64 evaluation (tools/diag_grade.py, seven seeing/L0 cases x five
@@ -184,9 +184,9 @@ PSFR_API int psfr_polyfit(psfr_ctx* ctx, int nseries, int nlam, const double* la
  * 1e-6 of the peak - the all-FP64 kernel and numpy differ by 1e-10 there.  A threshold >= the
  * cut disables the respective grade (e.g. 1e30). */
 enum { PSFR_OPT_EXP_CUT = 1, PSFR_OPT_EXP_GRADE = 2, PSFR_OPT_F32_ROWS = 3,
-       /* row kernel of the pruned stage B at dim 1280: 2 (default) one 160-thread group per row
-        * transform, data in shared memory (csrc/psfr_hot2.cu); 1 one warp per transform, data in
-        * registers (csrc/psfr_hot.cu, the only one at dim 2560) */
+       /* row kernel of the pruned stage B: 2 (default) one 128-thread group per row transform, data in
+        * shared memory, pruned third pass (csrc/psfr_hot2.cu); 1 one warp per transform, data in
+        * registers (csrc/psfr_hot.cu) */
        PSFR_OPT_ROW_KERNEL = 4 };
 PSFR_API int psfr_set_option(psfr_ctx* ctx, int key, double value);
 

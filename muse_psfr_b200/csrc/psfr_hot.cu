@@ -4,19 +4,21 @@
 // full N x N grid, inverse-transforms it and then reads only 80 rows x 80 columns of the
 // result (bilinear resampling to 40 x 40).  Here:
 //
-//  * hot_rows_kernel  - persistent, one CTA per SM.  Row pairs of the structure function D
+//  * row pass - group_rows_kernel (psfr_hot2.cu, the default) or hot_rows_kernel below
+//    (PSFR_OPT_ROW_KERNEL = 1): persistent, one CTA per SM.  Row pairs of the structure function D
 //    and of the telescope OTF (FP64 and FP32 copies) stream into a shared-memory ring with TMA
 //    bulk copies (cp.async.bulk + mbarrier complete_tx), issued by whichever warp releases a
 //    stage last.  A unit = one row pair at one wavelength: OTF rows = exp(-c_lambda D) * T
 //    evaluated straight from shared memory into registers (graded precision),
-//    one 1280-point warp FFT for the two packed real rows, and only the 80 sampled frequencies
-//    (+ mirrors) are untangled and written, as one 32-byte sector per frequency.  The eight
-//    warps run their units in lockstep rounds so that they share instruction fetches (3.10).
+//    one 1280-point warp FFT for the two packed real rows, and only the 40 kept frequencies
+//    (+ mirrors) are untangled and written, as one 32-byte sector per frequency.
+//    The eight warps run their units in lockstep rounds so that they share instruction fetches.
 //    D is read from HBM/L2 once per row pair for ALL wavelengths; the N x N OTF and PSF grids
 //    never exist in memory.
-//  * hot_cols pass    - 40 Hermitian column-pair transforms per PSF (summing the field
+//  * hot_cols pass    - 20 Hermitian column-pair transforms per PSF (summing the field
 //    directions of a draw before the transform: the mean over directions, psfrec.py:674,
-//    commutes with the linear transform), keeping the 80 sampled outputs -> 80x80 samples.
+//    commutes with the linear transform), keeping the 80 sampled outputs and their mirrors ->
+//    80x80 samples (the mirrored outputs fill the sample rows of the frequencies -kc).
 #include "pass_kernel.cuh"
 #include "fast_exp.cuh"
 #include "tma.cuh"
