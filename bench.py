@@ -369,13 +369,14 @@ def run_gpu(args):
     hot = {'ms': 0.0, 'n': 0, 'psfs': 0}
 
     gather_ev = []
+    h_fit_all = torch.empty((total, nlam, _lib.FIT_NPAR), dtype=torch.float64, pin_memory=True) if strong and g.rank == 0 else None
 
     def step_device():
         ctx.compute_batch(d_recs, dirs, pos, LBDA, out_cube=d_cube, out_fit=d_fit, stream=g.stream)
         if strong:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-            sharding.gather_grid(d_fit, total, nlam)        # NCCL gather of the fit records + D2H on rank 0
+            sharding.gather_grid(d_fit, total, nlam, host_out=h_fit_all)   # NCCL gather of the fit records + D2H on rank 0
             ev[1].record()
             gather_ev.append(ev)
 
@@ -416,7 +417,6 @@ def run_gpu(args):
     h_cube = torch.empty((nd, nlam, 40, 40), dtype=torch.float64, pin_memory=True)
     h_fit = torch.empty((nd, nlam, _lib.FIT_NPAR), dtype=torch.float64, pin_memory=True)
     gathered = {}
-    h_fit_all = torch.empty((total, nlam, _lib.FIT_NPAR), dtype=torch.float64, pin_memory=True) if strong and g.rank == 0 else None
 
     def step_e2e():
         if strong:
