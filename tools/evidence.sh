@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"group_rows|hot_cols|fit_kernel|fft_convolve|psd_quad|tiled_pass|ao_zone|resample" \
     -s 18 -c 9 -o $out/prof python bench.py --draws 256 --steps 1 --warmup 1 --no-cpu --no-configs --no-fp64-leg > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 PSFR_BENCH_BATCH_ONLY=1 ncu --set full --clock-control none --import-source on -k regex:"group_rows|hot_cols|pass_kernel" \
-    -s 12 -c 6 -o $out/prof_2560 python bench.py --config 5 --steps 1 --warmup 1 --no-cpu --draws5 16 > $out/ncu_2560.log 2>&1; echo "ncu 2560 rc=$?"
+    -s 19 -c 5 -o $out/prof_2560 python bench.py --config 5 --steps 1 --warmup 1 --no-cpu --draws5 16 > $out/ncu_2560.log 2>&1; echo "ncu 2560 rc=$?"
 python tools/cufft_check.py --out $out/cufft_strawman.json > $out/cufft.log 2>&1; echo "cufft rc=$?"
 python tools/parity_sweep.py --out $out/parity_sweep.json > $out/sweep.log 2>&1; echo "sweep rc=$?"
