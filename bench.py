@@ -90,9 +90,10 @@ def measured_peak():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.2):
         super().__init__(daemon=True)
         self.index = index
+        self.interval = interval
         self.rows = []
         self.stop_flag = threading.Event()
 
@@ -108,7 +109,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.stdout.strip().split(',')])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(self.interval)
 
     def summary(self):
         if not self.rows:
@@ -603,7 +604,7 @@ def run_config(args):
         g.close()
         return
     psfrec.set_device(g.local)
-    sampler = ClockSampler(g.local)
+    sampler = ClockSampler(g.local, interval=1.0)   # a millisecond-scale call: nvidia-smi queries stall the driver
     sampler.start()
     res = time_config(g, args, psfrec, _lib, args.config, steps=args.steps, warmup=args.warmup)
     sampler.stop_flag.set()
