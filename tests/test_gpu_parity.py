@@ -256,6 +256,17 @@ def test_psf_muse_wavelength_order_and_count(psfrec, psd1):
     assert_image_close(cube[40], ref[1])
 
 
+def test_psf_muse_random_wavelengths(psfrec, psd1):
+    """The kept-frequency / mirror tables are rebuilt per wavelength set: random
+    wavelengths, including ones where output pixels fall exactly on samples, against the oracle."""
+    rng = np.random.default_rng(2026)
+    lam = np.concatenate([rng.uniform(486, 1100, 9), [620.8, 776.0, 970.0]])   # npix = 1000, 800, 640: integer strides
+    got = psfrec.psf_muse(psd1[0], lam)
+    ref = orc.psf_muse(psd1[0], lam)
+    for k in range(lam.size):
+        assert_image_close(got[k], ref[k])
+
+
 def test_psf_muse_pruned_equals_full_grid(psfrec, psd1):
     """The pruned 80x80-sample transform against the full-grid PSF resampled on the host."""
     from scipy.interpolate import interpn
