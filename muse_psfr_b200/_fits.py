@@ -142,7 +142,11 @@ class _HDU:
 
     def copy(self):
         data = None if self.data is None else self.data.copy()
-        return type(self)(data=data, header=self.header)
+        new = type(self)(data=data, header=self.header)
+        # an extension read from a file travels verbatim (header cards such as TUNIT / TNULL / TSCAL and
+        # column types this reader only maps approximately, e.g. logical 'L', would not survive a rebuild)
+        new._raw = getattr(self, '_raw', None)
+        return new
 
     def writeto(self, fileobj, overwrite=False):
         hdus = [self] if isinstance(self, PrimaryHDU) else [PrimaryHDU(), self]
@@ -273,7 +277,12 @@ class HDUList(list):
         hdus = list(self)
         if not hdus or not isinstance(hdus[0], PrimaryHDU):
             hdus = [PrimaryHDU()] + hdus
-        for hdu in hdus:
+        for k, hdu in enumerate(hdus):
+            raw = getattr(hdu, '_raw', None)
+            if raw is not None and k > 0:
+                buf.write(raw[0])
+                buf.write(raw[1] + b'\0' * _pad(len(raw[1])))
+                continue
             cards = hdu._cards()
             cards += [_card(k, v, hdu.header.comments.get(k)) for k, v in hdu.header.items()
                       if not _is_structural(k) and v is not None]
@@ -418,6 +427,7 @@ def open(fileobj, only=None):    # noqa: A001 - mirrors astropy.io.fits.open
                     f.read(skip)
             if want:
                 hdus.append(_build_hdu(hdr, payload, first=not hdus))
+                hdus[-1]._raw = (raw, payload)      # see _HDU.copy
             else:
                 hdus.append(_HDU(data=None, header=Header((k, v) for k, v in hdr.items() if not _is_structural(k))))
         if not hdus:

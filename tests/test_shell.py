@@ -124,3 +124,27 @@ def test_package_exports():
                  'reconstruct_psf'):
         assert callable(getattr(pkg, name))
     assert pkg.__version__
+
+
+def test_copied_extension_travels_verbatim(tmp_path):
+    """the SPARTA extension copied into the result keeps header cards and column types this
+    reader does not model (TUNIT, TNULL, logical columns): it is re-emitted byte for byte."""
+    import io
+    from muse_psfr_b200 import _fits
+    cards = [_fits._card('XTENSION', 'BINTABLE'), _fits._card('BITPIX', 8), _fits._card('NAXIS', 2),
+             _fits._card('NAXIS1', 9), _fits._card('NAXIS2', 2), _fits._card('PCOUNT', 0), _fits._card('GCOUNT', 1),
+             _fits._card('TFIELDS', 2), _fits._card('TTYPE1', 'LGS1_SEEING'), _fits._card('TFORM1', 'D'),
+             _fits._card('TUNIT1', 'arcsec'), _fits._card('TTYPE2', 'FLAG'), _fits._card('TFORM2', 'L'),
+             _fits._card('EXTNAME', 'SPARTA_ATM_DATA'), 'END'.ljust(80)]
+    hdr = ''.join(cards).encode('ascii')
+    hdr += b' ' * _fits._pad(len(hdr))
+    payload = np.array([1.0, 0.8], dtype='>f8').tobytes()
+    rows = payload[:8] + b'T' + payload[8:] + b'F'
+    ext = hdr + rows + b'\0' * _fits._pad(len(rows))
+    primary = _fits.HDUList([_fits.PrimaryHDU()]).tobytes()
+    hdul = _fits.open(io.BytesIO(primary + ext))
+    assert list(hdul['SPARTA_ATM_DATA'].data['LGS1_SEEING']) == [1.0, 0.8]
+    out = _fits.HDUList([_fits.PrimaryHDU(), hdul['SPARTA_ATM_DATA'].copy()]).tobytes()
+    assert out[len(primary):] == ext
+    again = _fits.open(io.BytesIO(out))
+    assert again['SPARTA_ATM_DATA'].header.get('EXTNAME') == 'SPARTA_ATM_DATA'
