@@ -462,21 +462,21 @@ def run_gpu(args):
     chunk_planes = min(args.max_planes, nd)
     hot_launch, _ = own_bytes(info, chunk_planes, chunk_planes, nlam, 1280)
     _, step_bytes = own_bytes(info, nd, nd, nlam, 1280)
-    cfg = workload_config(args)
-    cfg.update({'chunk_planes': args.max_planes, 'draws_per_gpu': nd,
-                'sharding': ('strong: the %d draws are split over %d GPUs, fit records gathered to rank 0 (NCCL) '
-                             'inside the timed region' % (total, g.world)) if strong else
-                            ('single GPU' if g.world == 1 else 'weak: every rank runs its own %d-draw sweep' % total),
-                'exp_cut': 'OTF entries below exp(-%g) of the peak are flushed to zero (DESIGN.md 3.7)' % info['exp_cut'],
-                'graded_precision': 'row pairs entirely below exp(-%g) of the OTF peak are evaluated and transformed '
-                                    'in FP32, blocks entirely below exp(-%g) use the FP32 exp; everything else FP64 '
-                                    '(psfr.h PSFR_OPT_F32_ROWS / PSFR_OPT_EXP_GRADE; value_allfp64 = both off)'
-                                    % (info['f32_rows'], info['exp_grade'])})
+    cfg = workload_config(args)      # identical in both arms; what this run did beyond it goes to `run`
+    run = {'chunk_planes': args.max_planes, 'draws_per_gpu': nd,
+           'sharding': ('strong: the %d draws are split over %d GPUs, fit records gathered to rank 0 (NCCL) '
+                        'inside the timed region' % (total, g.world)) if strong else
+                       ('single GPU' if g.world == 1 else 'weak: every rank runs its own %d-draw sweep' % total),
+           'exp_cut': 'OTF entries below exp(-%g) of the peak are flushed to zero (DESIGN.md 3.7)' % info['exp_cut'],
+           'graded_precision': 'row pairs entirely below exp(-%g) of the OTF peak are evaluated and transformed '
+                               'in FP32, blocks entirely below exp(-%g) use the FP32 exp; everything else FP64 '
+                               '(psfr.h PSFR_OPT_F32_ROWS / PSFR_OPT_EXP_GRADE; value_allfp64 = both off)'
+                               % (info['f32_rows'], info['exp_grade'])}
     line = {
         'metric': METRIC, 'value': value, 'unit': 'PSF/s',
         'n_gpus': g.world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
         'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': cfg,
+        'data': 'synthetic', 'config': cfg, 'run': run,
         'e2e': {'value': e2e, 'unit': 'PSF/s',
                 'h2d_bytes_per_step': int(recs.nbytes + dirs.nbytes + pos.nbytes + LBDA.nbytes),
                 'd2h_bytes_per_step': int(h_cube.numel() * 8 + (total if strong else nd) * nlam * _lib.FIT_NPAR * 8),
