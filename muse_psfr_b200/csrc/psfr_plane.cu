@@ -91,6 +91,20 @@ constexpr int kFitWarps = 4;
 #ifndef PSFR_FIT_MINBLOCKS
 #define PSFR_FIT_MINBLOCKS 4
 #endif
+// The two-stage fit: pixel stride and squared relative-step tolerance of the coarse stage, squared
+// relative-step tolerance of the final stage = (1.49e-8)^2, the xtol at which MINPACK - the reference's
+// solver behind mpdaf - stops.  Measured on the 4480 images of a config-4 chunk (tools/fit_bench.py):
+// stride 4 / final 1e-9: 0.646 ms; stride 8: 0.600; final 1.49e-8: 0.610; both: 0.556 ms with FWHM / beta
+// within 1.5e-8 / 4.3e-8 of the tighter solution (bar 1e-5); strides 16 and 32 need more iterations than they save.
+#ifndef PSFR_FIT_COARSE_STEP
+#define PSFR_FIT_COARSE_STEP 8
+#endif
+#ifndef PSFR_FIT_COARSE_TOL2
+#define PSFR_FIT_COARSE_TOL2 1e-6
+#endif
+#ifndef PSFR_FIT_TOL2
+#define PSFR_FIT_TOL2 2.2e-16
+#endif
 constexpr int kNP = 5;
 constexpr int kNSUM = 21;  // 15 (J^T J upper) + 5 (J^T r) + 1 (cost)
 
@@ -246,7 +260,7 @@ __device__ __forceinline__ void chol_solve(const double (&L)[kNP][kNP], double* 
 
 // Levenberg-Marquardt on the pixel subset STEP from the start point x (updated in place);
 // sums holds the normal equations at the final x.  tol2 = square of the relative step at which
-// to stop (MINPACK, the reference's solver, stops at 1.49e-8; the final stage uses 1e-9).
+// to stop (MINPACK, the reference's solver, stops at 1.49e-8; so does the final stage).
 template <int STEP>
 __device__ __forceinline__ void lm_solve(const double* __restrict__ img, int npx, int nx, double* x, double* sums,
                                          double tol2, int max_iter, int& iter, int& status) {
@@ -378,13 +392,13 @@ fit_kernel(const double* __restrict__ imgs, int nimg, int ny, int nx, double* __
         x[3] = fwhm0 / (2.0 * sqrt(sqrt(2.0) - 1.0));
         x[4] = 2.0;
     }
-    // Stage 1: Levenberg-Marquardt on a quarter of the pixels down to a relative step of 1e-3 - it
+    // Stage 1: Levenberg-Marquardt on every eighth pixel down to a relative step of 1e-3 - it
     // only moves the start point (the converged minimum does not depend on it); stage 2: all
-    // pixels down to 1e-9.
+    // pixels down to MINPACK's own tolerance, 1.49e-8.
     int iter = 0, status = -1;
-    lm_solve<4>(img, npx, nx, x, sums, 1e-6, 12, iter, status);
+    lm_solve<PSFR_FIT_COARSE_STEP>(img, npx, nx, x, sums, PSFR_FIT_COARSE_TOL2, 12, iter, status);
     const int coarse_iter = iter;
-    lm_solve<1>(img, npx, nx, x, sums, 1e-18, 200, iter, status);
+    lm_solve<1>(img, npx, nx, x, sums, PSFR_FIT_TOL2, 200, iter, status);
     iter += coarse_iter;
     if (status > 0) status += coarse_iter;
     const int max_iter = 212;
