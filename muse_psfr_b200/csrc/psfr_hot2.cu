@@ -173,7 +173,7 @@ __device__ __forceinline__ double2 pass3(const Z2* buf, const P3Reg& e, int h) {
 // the rows pass 3 reads (see the file header for the index maps).  rowsA / rowsB: needed-row masks of the
 // transform (of the two halves of a packed pair).  Ends with the barrier that publishes pass 2.
 template <class Z, class TW>
-__device__ __forceinline__ void group_passes12(Z (&x)[kG1], Z* buf, const TW& tw, int b, int grp,
+__device__ __forceinline__ void group_passes12(Z (&x)[kG1], Z* buf, const TW& tw, int b, int br, int grp,
                                                const uint32_t* __restrict__ rowsA, const uint32_t* __restrict__ rowsB) {
     dft_any<kG1>(x);
     group_bar(grp);   // pass 3 of the previous transform is done with the buffer (these inputs were evaluated meanwhile)
@@ -188,15 +188,15 @@ __device__ __forceinline__ void group_passes12(Z (&x)[kG1], Z* buf, const TW& tw
     // warp hits eight distinct 16-byte slots), in place - a row belongs to one thread, so no barrier
     // inside - and only the outputs k2 that pass 3 will read are stored (the mask is the same for the
     // eight lanes of a quarter-warp: whole wavefronts are saved).
-    if (b < kP2Threads) {
-        Z* row = buf + (b >> 3) * kS1 + (b & 7) * kS2;
+    if (br < kP2Threads) {
+        Z* row = buf + (br >> 3) * kS1 + (br & 7) * kS2;
         Z z[kG2];
 #pragma unroll
         for (int i = 0; i < kG2; ++i) z[i] = row[i];
         dft_any<kG2>(z);
 #if PSFR_G_P2MASK
-        uint32_t need = __ldg(rowsA + (b >> 3));
-        if (rowsB != nullptr) need |= __ldg(rowsB + (b >> 3));
+        uint32_t need = __ldg(rowsA + (br >> 3));
+        if (rowsB != nullptr) need |= __ldg(rowsB + (br >> 3));
 #pragma unroll
         for (int i = 0; i < kG2; ++i)
             if ((need >> i) & 1) row[i] = z[i];
@@ -356,7 +356,11 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
         }
     };
 
-    const bool p3 = b >= kP3First, p3warp = b >= kP3First - 16;
+    // Role index of passes 2 and 3: the thread index rotated by one warp per group.  Pass 2 (the heavy one)
+    // runs on role threads 0..79, pass 3 on 48..127; a scheduler holds the same warp of every group, so
+    // without the rotation two of the four schedulers would carry every group's pass 2.
+    const int br = (b + 32 * grp) % kGT;
+    const bool p3 = br >= kP3First, p3warp = br >= kP3First - 16;
 #pragma unroll 1
     for (;;) {
         int rel = base + grp;
@@ -422,13 +426,13 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     }
                 }
                 Z2* zbuf = reinterpret_cast<Z2*>(buf);
-                group_passes12(x, zbuf, twp, b, grp, p.rows + lamA * kGMaskStride, p.rows + lamB * kGMaskStride);
+                group_passes12(x, zbuf, twp, b, br, grp, p.rows + lamA * kGMaskStride, p.rows + lamB * kGMaskStride);
                 // the pass-3 threads fetch their records while pass 2 runs
                 P3Reg ea, eb;
                 ea.col = eb.col = 0;
                 if (p3) {
-                    ea = fetch_p3<1>(p.p3 + (size_t)lamA * 2 * kNC + (b - kP3First));
-                    eb = fetch_p3<1>(p.p3 + (size_t)lamB * 2 * kNC + (b - kP3First));
+                    ea = fetch_p3<1>(p.p3 + (size_t)lamA * 2 * kNC + (br - kP3First));
+                    eb = fetch_p3<1>(p.p3 + (size_t)lamB * 2 * kNC + (br - kP3First));
                 }
                 group_bar(grp);
                 if (p3warp) {
@@ -518,8 +522,8 @@ group_rows_kernel(Rows2Params p, const double2* __restrict__ g_tw) {
                     }
                 }
             }
-            group_passes12(x, buf, twr, b, grp, need, nullptr);
-            if (sub == 0 && p3) e = fetch_p3<NF>(p.p3 + (size_t)lam * 2 * kNC + (b - kP3First));
+            group_passes12(x, buf, twr, b, br, grp, need, nullptr);
+            if (sub == 0 && p3) e = fetch_p3<NF>(p.p3 + (size_t)lam * 2 * kNC + (br - kP3First));
             group_bar(grp);
             if (p3) {
                 const double2 a = pass3(buf, e, 0);
