@@ -433,6 +433,12 @@ def compute_psf_batch(lbda, seeing, GL, L0, npsflin=1, h=(100, 10000), three_lgs
     lam = np.atleast_1d(np.asarray(lbda, dtype=float))
     seeing, GL, L0 = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (seeing, GL, L0))
     nd = seeing.size
+    if GL.size != nd or L0.size != nd:
+        raise ValueError('seeing, GL and L0 must have one entry per draw (got %d, %d, %d)' % (nd, GL.size, L0.size))
+    if nd == 0 or lam.size == 0:
+        # nothing to compute: empty results of the right shape, written through nothing
+        return (np.empty((nd, lam.size, _lib.FIT_NPAR)),
+                np.empty((nd, lam.size, _lib.PSF_DIM, _lib.PSF_DIM)) if want_cube else None)
     if nd <= 64:
         # scalar expressions, bit-identical to the reference's own scalars
         h_arr = np.array(h)

@@ -163,3 +163,15 @@ def test_caller_buffers_are_validated_at_the_binding():
         _lib.checked_ptr(t[::2], 10, 0, 'out_fit', True)
     with pytest.raises(TypeError):
         _lib.checked_ptr([1.0, 2.0], 2, 0, 'out_fit', True)
+
+
+def test_empty_and_ragged_batches(built_lib):
+    """No draws / no wavelengths give empty results of the right shape without touching the device;
+    parameter arrays of different lengths are refused before anything is computed."""
+    lam = np.linspace(490, 930, 35)
+    fit, cube = psfrec.compute_psf_batch(lam, [], [], [])
+    assert fit.shape == (0, 35, _lib.FIT_NPAR) and cube.shape == (0, 35, 40, 40)
+    fit, cube = psfrec.compute_psf_batch([], [1.0], [0.7], [25.], want_cube=False)
+    assert fit.shape == (1, 0, _lib.FIT_NPAR) and cube is None
+    with pytest.raises(ValueError, match='one entry per draw'):
+        psfrec.compute_psf_batch(lam, [1.0, 0.8], [0.7], [25., 20.])
