@@ -22,7 +22,8 @@ def built_lib():
 
 
 def test_header_and_binding_agree():
-    hdr = open(os.path.join(ROOT, 'include', 'psfr.h')).read()
+    with open(os.path.join(ROOT, 'include', 'psfr.h')) as f:
+        hdr = f.read()
     declared = set(re.findall(r'PSFR_API\s+[\w\s\*]+?\b(psfr_\w+)\s*\(', hdr))
     assert declared == set(_lib.exported_symbols())
     # record layouts
